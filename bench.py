@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: clFFT forward 8192-pt gr_complex (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the clFFT hot path over one batch of synthetic vectors
+(`--nvec` vectors of 8192 gr_complex per GPU; default 8192 vectors = 512 MiB in + 512 MiB
+out, larger than the 126 MB L2, so no L2 flush is needed between steps).
+
+  value     device-resident throughput (inputs in HBM), Msamples/s over all ranks, CUDA events
+  e2e       same metric through the C ABI with pinned HOST buffers: clb200_fft_work() does
+            H2D -> kernel -> D2H inside the timed region
+  roofline  the FFT kernel against MEASURED_PEAKS.json's HBM copy bandwidth, 16 B/sample
+  cpu_baseline  the oracle (C restatement of the reference CPU path) on the host cores
+  blocks    device-resident throughput of the other hot-path blocks (secondary, same run)
+
+Multi-GPU: clFFT streams/vectors are independent (lib/clFFT_impl.cc:537-541) so ranks
+shard vectors with no collective ("weak" scaling: per-GPU work fixed).  torch is used only for
+device memory, streams/events and torch.distributed; every kernel is ours.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FFT_N = 8192
+BYTES_PER_SAMPLE = 16          # 8 B read + 8 B written per gr_complex sample
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nvec", type=int, default=8192, help="8192-pt vectors per GPU per step")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the secondary per-block numbers")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def rd():
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        self.thr = threading.Thread(target=rd, daemon=True)
+        self.thr.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's restatement of clFFT_impl::testCPU
+# (lib/clFFT_impl.cc:464-518; FFTW3f is not in the image) on the host cores
+# --------------------------------------------------------------------------------
+def cpu_fft_run(nvec, reps, threads):
+    import numpy as np
+    from oracle import oracle as orc
+    orc.lib().orc_set_threads(threads)
+    x = orc.rng_c32(FFT_N * nvec, orc.SEED_F)
+    orc.fft(x[:FFT_N * min(nvec, 64)], FFT_N, -1)           # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.fft(x, FFT_N, -1)
+    dt = time.perf_counter() - t0
+    return FFT_N * nvec * reps / dt / 1e6, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (restated; kind 'port') on all host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    orc.lib().orc_set_threads(cores)
+    threads = orc.lib().orc_num_threads()
+    nvec = 2048                                            # bounded sample: 16 Mi samples per step
+    import numpy as np
+    x = orc.rng_c32(FFT_N * nvec, orc.SEED_F)
+    for _ in range(max(1, min(args.warmup, 3))):
+        orc.fft(x, FFT_N, -1)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.fft(x, FFT_N, -1)
+    dt = time.perf_counter() - t0
+    val = FFT_N * nvec * steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "Msamples/sec per block (clFFT forward 8192-pt)",
+        "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "clFFT forward 8192-pt gr_complex, 1 stream (BASELINE configs[1])",
+                   "fft_size": FFT_N, "vectors_per_step": nvec},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                         "sample": "%d vectors of 8192 per step, oracle radix-2 FFT (FFTW3f of the "
+                                   "reference is not in the image), OpenMP over vectors" % nvec},
+        "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------
+def secondary_blocks(torch, blocks, capi, dev, stream_ptr, hbm_peak):
+    """device-resident throughput of the other blocks, a few launches each (not the headline)"""
+    import numpy as np
+    from oracle import oracle as orc
+    out = {}
+    gpu = (1, 2, 0, dev)
+
+    def timeit(fn, iters=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters / 1e3
+
+    n = 1 << 26                                     # 64 Mi complex samples = 512 MiB
+    a = torch.empty(n * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
+    b = torch.empty(n * 2, dtype=torch.float32, device="cuda")
+    try:
+        blk = blocks.clMathConst(capi.DTYPE_COMPLEX, *gpu, 0.7071, capi.OP_MULTIPLY)
+        t = timeit(lambda: blk.launch_device(a.data_ptr(), b.data_ptr(), n, stream_ptr))
+        out["clMultiplyConst"] = {"Msamples_s": n / t / 1e6, "GBps": 16 * n / t / 1e9, "frac_hbm": 16 * n / t / 1e9 / hbm_peak}
+    except Exception as e:                           # noqa: BLE001
+        out["clMultiplyConst"] = {"error": str(e)}
+    try:
+        taps = np.zeros(256, np.float32)
+        taps[:255] = orc.firdes_low_pass_hamming(1.0, 30e6, 1.5e6, 283000.0)
+        for name, ut in (("clFilter_fft_256tap", False), ("clFilter_fir_256tap", True)):
+            blk = blocks.clFilter(*gpu, 1, taps, 1, 0, ut)
+            t = timeit(lambda: blk.launch_device(a.data_ptr(), n, b.data_ptr(), stream_ptr), 3)
+            out[name] = {"Msamples_s": n / t / 1e6, "GBps": 16 * n / t / 1e9, "frac_hbm": 16 * n / t / 1e9 / hbm_peak}
+    except Exception as e:                           # noqa: BLE001
+        out["clFilter"] = {"error": str(e)}
+    try:
+        M = 64
+        ptaps = np.zeros(128, np.float32)
+        ptaps[:127] = orc.firdes_low_pass_hamming(1.0, 64.0, 0.5, 1.21)
+        niter = (n - 128) // M
+        blk = blocks.clPolyphaseChannelizer(*gpu, ptaps, 65536, M, M, list(range(M)))
+        t = timeit(lambda: blk.launch_device(a.data_ptr(), b.data_ptr(), niter, stream_ptr), 3)
+        out["clPolyphaseChannelizer_64ch"] = {"Msamples_s": niter * M / t / 1e6, "GBps": 16 * niter * M / t / 1e9,
+                                              "frac_hbm": 16 * niter * M / t / 1e9 / hbm_peak}
+    except Exception as e:                           # noqa: BLE001
+        out["clPolyphaseChannelizer_64ch"] = {"error": str(e)}
+    del a, b
+    try:
+        A, F, T = 32, 1024, 1024
+        nb = T * A * F * 2
+        bufs = [torch.randint(-127, 128, (nb,), dtype=torch.int8, device="cuda") for _ in range(4)]   # 256 MiB > L2
+        vis = torch.empty(F * (A * (A + 1) // 2) * 2, dtype=torch.float32, device="cuda")
+        blk = blocks.clXEngine(*gpu, False, capi.DTYPE_BYTE, 1, A, 1, 0, F, T, [])
+        it = [0]
+        def f():
+            blk.launch_device(bufs[it[0] % 4].data_ptr(), vis.data_ptr(), False, stream_ptr)
+            it[0] += 1
+        t = timeit(f, 8)
+        bytes_ = nb + vis.numel() * 4
+        out["clXEngine_32st_1024ch_int1024"] = {
+            "Msamples_s": A * F * T / t / 1e6, "us_per_integration": t * 1e6, "GBps": bytes_ / t / 1e9,
+            "frac_hbm": bytes_ / t / 1e9 / hbm_peak, "int8_TOPS": 2.0 * 64 * 64 * T * F / t / 1e12}
+    except Exception as e:                           # noqa: BLE001
+        out["clXEngine_32st_1024ch_int1024"] = {"error": str(e)}
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    from gr_clenabled_b200 import blocks, capi
+
+    capi.require_gpu()                       # no CPU fallback: fail loudly without the CUDA path
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = peaks()
+
+    nvec, N = args.nvec, FFT_N
+    nsamp = nvec * N
+    # device-resident batch (synthetic uniform [-1,1) gr_complex), in != out, 2 x 512 MiB > L2
+    x = torch.empty(nsamp * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
+    y = torch.empty_like(x)
+    fft = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, 1, 2, 0, local)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step():
+        fft.launch_device(x.data_ptr(), y.data_ptr(), nvec, sp)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = fft.counters()["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = fft.counters()["launches"] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * nsamp / (ms_per_step / 1e3) / 1e6          # Msamples/s, all ranks
+    kernel_s = ms_per_step / 1e3                                # one launch per step
+    achieved = BYTES_PER_SAMPLE * nsamp / kernel_s / 1e9
+
+    # parity spot check of what was just timed (first and last vector) against numpy's FFT
+    yh = y.view(torch.complex64)
+    for v in (0, nvec - 1):
+        got = yh[v * N:(v + 1) * N].cpu().numpy()
+        want = np.fft.fft(x.view(torch.complex64)[v * N:(v + 1) * N].cpu().numpy().astype(np.complex128))
+        err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+        if not err < 1e-5:
+            raise SystemExit("bench: FFT output does not match (rel err %g)" % err)
+
+    # ---- e2e: pinned host buffers through clb200_fft_work (H2D + kernel + D2H timed) ----
+    hx = torch.empty(nsamp * 2, dtype=torch.float32).pin_memory()
+    hy = torch.empty(nsamp * 2, dtype=torch.float32).pin_memory()
+    hx.uniform_(-1, 1)
+    for _ in range(2):
+        fft.work_ptr(hx.data_ptr(), hy.data_ptr(), nvec)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fft.work_ptr(hx.data_ptr(), hy.data_ptr(), nvec)       # returns with outputs on the host
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_val = world * nsamp * e2e_steps / dt / 1e6
+    got = hy.view(torch.complex64)[:N].numpy()
+    want = np.fft.fft(hx.view(torch.complex64)[:N].numpy().astype(np.complex128))
+    if not float(np.max(np.abs(got - want)) / np.max(np.abs(want))) < 1e-5:
+        raise SystemExit("bench: e2e FFT output does not match")
+    del hx, hy
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_blocks:
+        del x, y
+        torch.cuda.empty_cache()
+        extra = secondary_blocks(torch, blocks, capi, local, sp, hbm_peak)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v1, _ = cpu_fft_run(512, 2, 1)
+        reps = 4
+        vN, dtN = cpu_fft_run(2048, reps, cores)
+        cpu = {"value": vN, "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "single_thread_value": v1,
+               "sample": "%d x %d vectors of 8192 (%.1f s); oracle radix-2 FFT restating "
+                         "clFFT_impl::testCPU, FFTW3f absent from the image" % (reps, 2048, dtN)}
+
+    if rank == 0:
+        line = {
+            "metric": "Msamples/sec per block (clFFT forward 8192-pt)",
+            "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "clFFT forward 8192-pt gr_complex, 1 stream per GPU (BASELINE configs[1])",
+                       "fft_size": N, "vectors_per_step_per_gpu": nvec,
+                       "l2": "inputs larger than L2 (2 x %d MiB per step), no flush needed" % (nsamp * 8 >> 20),
+                       "parallelism": "vectors sharded over %d GPU(s), no collective" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_fft<13,...>", "bytes_per_launch": BYTES_PER_SAMPLE * nsamp},
+            "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": nsamp * 8,
+                    "d2h_bytes_per_step": nsamp * 8, "steps": e2e_steps,
+                    "api": "clb200_fft_work (pinned host in/out)"},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if extra:
+            line["blocks"] = extra
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,299 @@
+// fft.cu -- clFFT block: batched 1-D complex FFT (window, shift fused), sm_100a.
+//
+// Replaces clFFT_impl::processOpenCL (lib/clFFT_impl.cc:526-634): where the
+// reference issues, per vector, an H2D copy, an optional MultiplyFloat window
+// kernel (:202-229), one clfftEnqueueTransform with batch 1 (:583), a D2H copy
+// and then a host memcpy fftshift (:594-607), this does every vector of a
+// work() call in ONE launch: the window multiply is fused into the first
+// pass' HBM load, the backward-shift into its load index (:548-553) and the
+// forward-shift into the last pass' store index.
+//
+// HBM traffic: 8 B read + 8 B written per sample = 16 B/sample (algorithmic
+// minimum); the transform itself lives in shared memory/registers.
+#include "common.cuh"
+#include "fft_device.cuh"
+#include <cmath>
+#include <cstdlib>
+
+using namespace clb200;
+using namespace clb200::fftdev;
+
+namespace {
+
+enum : int { F_INVERSE = 1, F_SHIFT = 2, F_REAL_IN = 4 };
+
+template <int LOGN, int EPT, int BATCH, int MINB>
+__global__ void __launch_bounds__((1 << LOGN) / EPT * BATCH, MINB)
+k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
+      const float2 *__restrict__ tw, const float *__restrict__ win, int flags)
+{
+    using P = Plan<LOGN, EPT>;
+    constexpr int N = P::N, T = P::T;
+    extern __shared__ __align__(16) float2 smem[];
+
+    const int tb = (BATCH == 1) ? 0 : threadIdx.x / T;     // transform within the CTA
+    const int lt = (BATCH == 1) ? threadIdx.x : threadIdx.x % T;
+    float2 *buf = smem + tb * P::SMEM_F2;
+    const bool inverse = flags & F_INVERSE;
+    const bool real_in = flags & F_REAL_IN;
+    // forward+shift swaps the OUTPUT halves, backward+shift swaps the INPUT halves
+    const int in_xor = ((flags & F_SHIFT) && inverse) ? (N >> 1) : 0;
+    const int out_xor = ((flags & F_SHIFT) && !inverse) ? (N >> 1) : 0;
+
+    const long ntile = (nvec + BATCH - 1) / BATCH;
+    for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long v = tile * BATCH + tb;
+        const bool active = v < nvec;
+        const float2 *src = in + v * N;
+        const float *srcf = reinterpret_cast<const float *>(in) + v * N;
+        float2 *dst = out + v * N;
+        float2 x[EPT];
+
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < EPT; e++) {
+                const int idx = in_index<P, EPT>(lt, e);
+                if (real_in) x[e] = make_float2(__ldcs(srcf + (idx ^ in_xor)), 0.0f);
+                else x[e] = __ldcs(src + (idx ^ in_xor));
+            }
+            if (win != nullptr) {
+#pragma unroll
+                for (int e = 0; e < EPT; e++) {
+                    const float w = __ldg(win + in_index<P, EPT>(lt, e));
+                    x[e].x *= w;
+                    x[e].y *= w;
+                }
+            }
+            if (inverse) {
+#pragma unroll
+                for (int e = 0; e < EPT; e++) x[e] = make_float2(x[e].y, x[e].x);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+        }
+
+        fft_core<P, EPT>(x, buf, lt, tw);
+
+        if (active) {
+            for_each_output<P, EPT>(x, lt, [&](int o, float2 a) {
+                if (inverse) a = make_float2(a.y, a.x);
+                __stcs(dst + (o ^ out_xor), a);
+            });
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host ----
+struct FftVariant {
+    int logn, ept, batch, threads, smem_bytes, tw_total, max_ctas_per_sm;
+    void (*fill_tw)(std::vector<float2> &);
+    void (*kernel)(const float2 *, float2 *, long, const float2 *, const float *, int);
+};
+
+template <int LOGN, int EPT>
+void fill_tw_t(std::vector<float2> &tw)
+{
+    using P = Plan<LOGN, EPT>;
+    tw.assign(std::max(1, P::TW_TOTAL), make_float2(1.f, 0.f));
+    for (int p = 1; p < P::npass(); p++) {
+        int R = P::radix(p), NS = P::ns(p), off = P::tw_offset(p);
+        for (int r = 1; r < R; r++)
+            for (int k = 0; k < NS; k++) {
+                double a = -2.0 * M_PI * (double)r * (double)k / ((double)NS * (double)R);
+                tw[off + (r - 1) * NS + k] = make_float2((float)cos(a), (float)sin(a));
+            }
+    }
+}
+
+template <int LOGN, int EPT, int BATCH, int MINB>
+FftVariant make_variant()
+{
+    using P = Plan<LOGN, EPT>;
+    FftVariant v;
+    v.logn = LOGN;
+    v.ept = EPT;
+    v.batch = BATCH;
+    v.threads = P::T * BATCH;
+    v.smem_bytes = P::SMEM_F2 * BATCH * (int)sizeof(float2);
+    v.tw_total = P::TW_TOTAL;
+    v.max_ctas_per_sm = MINB;
+    v.fill_tw = &fill_tw_t<LOGN, EPT>;
+    v.kernel = &k_fft<LOGN, EPT, BATCH, MINB>;
+    return v;
+}
+
+// default instantiation per size; alternates selectable with CLB200_FFT_VARIANT
+// (used by the tuning script).  {LOGN, EPT, transforms per CTA, min CTAs/SM}
+const FftVariant *pick_variant(int logn)
+{
+    static const FftVariant tab[] = {
+        make_variant<1, 2, 128, 4>(),   make_variant<2, 4, 128, 4>(),  make_variant<3, 8, 128, 4>(),
+        make_variant<4, 4, 32, 4>(),    make_variant<5, 8, 32, 4>(),   make_variant<6, 8, 32, 4>(),
+        make_variant<7, 8, 16, 4>(),    make_variant<8, 16, 16, 2>(),  make_variant<9, 8, 4, 4>(),
+        make_variant<10, 16, 4, 2>(),   make_variant<11, 16, 2, 2>(),  make_variant<12, 16, 1, 2>(),
+        make_variant<13, 16, 1, 2>(),   make_variant<14, 16, 1, 1>(),
+    };
+    static const FftVariant alt[] = {
+        make_variant<13, 32, 1, 2>(),   // CLB200_FFT_VARIANT=1
+        make_variant<13, 32, 1, 1>(),   // 2
+        make_variant<13, 16, 1, 1>(),   // 3
+        make_variant<13, 8, 1, 1>(),    // 4
+        make_variant<13, 8, 1, 2>(),    // 5
+    };
+    if (logn == 13) {
+        const char *e = getenv("CLB200_FFT_VARIANT");
+        int a = e ? atoi(e) : 0;
+        if (a >= 1 && a <= (int)(sizeof(alt) / sizeof(alt[0]))) return &alt[a - 1];
+    }
+    if (logn < 1 || logn > 14) return nullptr;
+    return &tab[logn - 1];
+}
+
+struct Fft : clb200_block {
+    int n = 0, logn = 0, dir = 0, dtype = 0, shift = 0;
+    bool has_window = false;
+    const FftVariant *var = nullptr;
+    Buf d_tw, d_win;
+    int resident = 1;     // CTAs per SM the launch is sized for
+    ~Fft() override
+    {
+        DeviceGuard g(device);
+        d_tw.release();
+        d_win.release();
+    }
+};
+
+int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
+{
+    if (nvec <= 0) return CLB200_OK;
+    const FftVariant *v = f->var;
+    int flags = (f->dir > 0 ? F_INVERSE : 0) | (f->shift ? F_SHIFT : 0) |
+                (f->dtype == CLB200_DTYPE_FLOAT ? F_REAL_IN : 0);
+    long ntile = (nvec + v->batch - 1) / v->batch;
+    int grid = grid_for(ntile, device_sm_count(f->device), f->resident);
+    v->kernel<<<grid, v->threads, v->smem_bytes, st>>>(
+        (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
+        f->has_window ? (const float *)f->d_win.p : nullptr, flags);
+    CLB_CUDA(cudaGetLastError());
+    f->n_launch++;
+    return CLB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int clb200_fft_create(int fft_size, int dir, const float *window, int window_len, int dtype,
+                      int device, int shift, clb200_handle *out)
+{
+    CLB_CHECK(out != nullptr, CLB200_EINVAL, "null out");
+    CLB_CHECK(fft_size >= 2 && (fft_size & (fft_size - 1)) == 0 && fft_size <= 16384, CLB200_EINVAL,
+              "clFFT: fft size %d is not a power of two in 2..16384", fft_size);
+    CLB_CHECK(dir == CLB200_FFT_FORWARD || dir == CLB200_FFT_BACKWARD, CLB200_EINVAL,
+              "clFFT: direction must be -1 (forward) or 1 (backward), got %d", dir);
+    // lib/clFFT_impl.cc:74-76: "window not the same length as fft_size"
+    CLB_CHECK(window_len == 0 || window_len == fft_size, CLB200_EINVAL,
+              "clFFT: window not the same length as fft_size (%d vs %d)", window_len, fft_size);
+    CLB_CHECK(window_len == 0 || window != nullptr, CLB200_EINVAL, "clFFT: null window");
+    CLB_CHECK(dtype == CLB200_DTYPE_COMPLEX || dtype == CLB200_DTYPE_FLOAT, CLB200_EINVAL,
+              "clFFT: data type must be complex or float, got %d", dtype);
+    CLB_CHECK(dtype == CLB200_DTYPE_COMPLEX || dir == CLB200_FFT_FORWARD, CLB200_EINVAL,
+              "clFFT: real input is forward-only");
+    int n = clb200_device_count();
+    CLB_CHECK(n > 0, CLB200_ECUDA, "no CUDA device present");
+    CLB_CHECK(device >= 0 && device < n, CLB200_EINVAL, "device %d out of range", device);
+
+    DeviceGuard g(device);
+    Fft *f = new Fft;
+    f->kind = KIND_FFT;
+    f->device = device;
+    f->n = fft_size;
+    f->logn = ilog2(fft_size);
+    f->dir = dir;
+    f->dtype = dtype;
+    f->shift = shift ? 1 : 0;
+    f->var = pick_variant(f->logn);
+    auto fail = [&](int rc) {
+        delete f;
+        return rc;
+    };
+    if (!f->var) {
+        set_error("clFFT: no kernel for size %d", fft_size);
+        return fail(CLB200_EINVAL);
+    }
+    std::vector<float2> tw;
+    f->var->fill_tw(tw);
+    if (f->d_tw.reserve(tw.size() * sizeof(float2)) != CLB200_OK) return fail(CLB200_ENOMEM);
+    if (cudaMemcpy(f->d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) !=
+        cudaSuccess) {
+        set_error("clFFT: twiddle upload failed");
+        return fail(CLB200_ECUDA);
+    }
+    if (window_len) {
+        f->has_window = true;
+        if (f->d_win.reserve(sizeof(float) * fft_size) != CLB200_OK) return fail(CLB200_ENOMEM);
+        if (cudaMemcpy(f->d_win.p, window, sizeof(float) * fft_size, cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+            set_error("clFFT: window upload failed");
+            return fail(CLB200_ECUDA);
+        }
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void *)f->var->kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         f->var->smem_bytes);
+    if (e != cudaSuccess) {
+        set_error("clFFT: cannot reserve %d B of shared memory: %s", f->var->smem_bytes,
+                  cudaGetErrorString(e));
+        return fail(CLB200_ECUDA);
+    }
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)f->var->kernel,
+                                                      f->var->threads, f->var->smem_bytes);
+    if (e != cudaSuccess || occ < 1) {
+        set_error("clFFT: kernel for size %d does not fit an SM (%s)", fft_size,
+                  cudaGetErrorString(e));
+        return fail(CLB200_ECUDA);
+    }
+    f->resident = occ;
+    *out = f;
+    return CLB200_OK;
+}
+
+int clb200_fft_launch_device(clb200_handle h, const void *d_in, void *d_out, long nvec, void *stream)
+{
+    Fft *f;
+    CLB_TRY(check_kind(h, KIND_FFT, &f));
+    CLB_CHECK(nvec >= 0, CLB200_EINVAL, "negative vector count");
+    DeviceGuard g(f->device);
+    return fft_launch(f, d_in, d_out, nvec, (cudaStream_t)stream);
+}
+
+int clb200_fft_work(clb200_handle h, const void *in, void *out, long nvec)
+{
+    Fft *f;
+    CLB_TRY(check_kind(h, KIND_FFT, &f));
+    CLB_CHECK(nvec >= 0, CLB200_EINVAL, "negative vector count");
+    if (nvec == 0) return CLB200_OK;
+    DeviceGuard g(f->device);
+    PortDesc pd;
+    pd.nin = pd.nout = 1;
+    pd.in[0] = in;
+    pd.out[0] = out;
+    pd.in_bytes[0] = (size_t)f->n * (f->dtype == CLB200_DTYPE_FLOAT ? 4 : 8);
+    pd.out_bytes[0] = (size_t)f->n * 8;
+    return run_chunked(f, pd, nvec, chunk_for(pd),
+                       [&](const void **di, void **dout, long n, cudaStream_t st, long *) {
+                           return fft_launch(f, di[0], dout[0], n, st);
+                       });
+}
+
+int clb200_fft_work_streams(clb200_handle h, const void *const *in, void *const *out, int nstreams,
+                            long nvec)
+{
+    CLB_CHECK(nstreams >= 1 && in && out, CLB200_EINVAL, "bad stream list");
+    for (int s = 0; s < nstreams; s++) CLB_TRY(clb200_fft_work(h, in[s], out[s], nvec));
+    return CLB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,252 @@
+// fft_device.cuh -- device building blocks of the hand-written FFT.
+//
+// The arithmetic that clFFT (clfftEnqueueTransform, lib/clFFT_impl.cc:583) and
+// FFTW (lib/fft.cc:175-179) do for the reference is done here by a Stockham
+// autosort FFT:  N = R0*R1*...; pass p with Ns = R0*..*R(p-1):
+//     for j in [0, N/R):  k = j mod Ns
+//         v[r] = x[j + r*N/R] * exp(-2*pi*i * r*k / (Ns*R))        r = 0..R-1
+//         V    = DFT_R(v)
+//         y[(j-k)*R + k + r*Ns] = V[r]
+// Radix-R butterflies (R = 2..32) run entirely in registers as unrolled
+// radix-2 DIF stages with compile-time twiddles; passes exchange data through
+// padded shared memory; the first pass reads HBM directly (coalesced float2)
+// and the last pass writes HBM directly, so each sample crosses HBM exactly
+// once in each direction (16 B/sample).
+//
+// The inverse transform is the forward one on data with re/im swapped on load
+// and on store (IDFT(x) = swap(DFT(swap(x)))), so only forward twiddles exist.
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+#include <utility>
+
+namespace clb200 {
+namespace fftdev {
+
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+
+__host__ __device__ constexpr int bitrev(int v, int bits)
+{
+    int r = 0;
+    for (int b = 0; b < bits; b++)
+        if (v & (1 << b)) r |= 1 << (bits - 1 - b);
+    return r;
+}
+
+// cos(2*pi*k/32), k = 0..8, correctly rounded literals
+__host__ __device__ constexpr float cos32_q(int k)
+{
+    constexpr float c[9] = {1.0f,
+                            0.98078528040323044913f,
+                            0.92387953251128675613f,
+                            0.83146961230254523708f,
+                            0.70710678118654752440f,
+                            0.55557023301960222474f,
+                            0.38268343236508977173f,
+                            0.19509032201612826785f,
+                            0.0f};
+    return c[k];
+}
+__host__ __device__ constexpr float cos32(int k)
+{
+    k = ((k % 32) + 32) % 32;
+    if (k > 16) k = 32 - k;
+    return k > 8 ? -cos32_q(16 - k) : cos32_q(k);
+}
+__host__ __device__ constexpr float sin32(int k) { return cos32(k - 8); }
+
+// a * W_32^K  (W = exp(-2*pi*i/32)), K compile-time
+template <int K>
+__device__ __forceinline__ float2 mul_w32(float2 a)
+{
+    constexpr int k = ((K % 32) + 32) % 32;
+    if constexpr (k == 0) return a;
+    else if constexpr (k == 8) return make_float2(a.y, -a.x);
+    else if constexpr (k == 16) return make_float2(-a.x, -a.y);
+    else if constexpr (k == 24) return make_float2(-a.y, a.x);
+    else if constexpr (k == 4) {
+        constexpr float s = cos32(4);
+        return make_float2((a.x + a.y) * s, (a.y - a.x) * s);
+    } else if constexpr (k == 12) {
+        constexpr float s = cos32(4);
+        return make_float2((a.y - a.x) * s, -(a.x + a.y) * s);
+    } else {
+        constexpr float wr = cos32(k), wi = -sin32(k);
+        return make_float2(fmaf(-a.y, wi, a.x * wr), fmaf(a.y, wr, a.x * wi));
+    }
+}
+
+// In-register forward DFT of x[OFF .. OFF+R): radix-2 decimation in frequency.
+// Result is left in bit-reversed order: X[k] = x[OFF + bitrev(k)].
+template <int R, int OFF, int NREG>
+__device__ __forceinline__ void dft_dif(float2 (&x)[NREG])
+{
+    constexpr int LR = ilog2(R);
+    static_for<0, LR>([&](auto s_) {
+        constexpr int s = decltype(s_)::value;
+        constexpr int h = R >> (s + 1);
+        static_for<0, R / 2>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            constexpr int g = b / h, i = b % h;
+            constexpr int ia = OFF + g * 2 * h + i, ib = ia + h;
+            float2 a = x[ia], c = x[ib];
+            x[ia] = make_float2(a.x + c.x, a.y + c.y);
+            float2 d = make_float2(a.x - c.x, a.y - c.y);
+            x[ib] = mul_w32<i * (16 / h)>(d);
+        });
+    });
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+{
+    return make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
+}
+
+// shared-memory padding: 16 B after every 128 B (float2 units) keeps the
+// stride-R stores of the first pass and the unit-stride loads conflict-free
+__host__ __device__ constexpr int pad(int i) { return i + ((i >> 4) << 1); }
+
+// Compile-time radix plan: greedy, largest radices first.
+template <int LOGN, int EPT>
+struct Plan {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int T = N / EPT;             // threads per transform
+    __host__ __device__ static constexpr int npass()
+    {
+        int rem = N, n = 0;
+        while (rem > 1) {
+            rem /= (rem < EPT ? rem : EPT);
+            n++;
+        }
+        return n;
+    }
+    __host__ __device__ static constexpr int ns(int p)      // product of earlier radices
+    {
+        int rem = N, s = 1;
+        for (int i = 0; i < p; i++) {
+            int r = rem < EPT ? rem : EPT;
+            rem /= r;
+            s *= r;
+        }
+        return s;
+    }
+    __host__ __device__ static constexpr int radix(int p)
+    {
+        int rem = N / ns(p);
+        return rem < EPT ? rem : EPT;
+    }
+    __host__ __device__ static constexpr int tw_offset(int p)   // float2 units, passes >= 1
+    {
+        int off = 0;
+        for (int i = 1; i < p; i++) off += (radix(i) - 1) * ns(i);
+        return off;
+    }
+    static constexpr int TW_TOTAL = tw_offset(npass());
+    static constexpr int SMEM_F2 = npass() > 1 ? pad(N) : 0;    // float2 per transform
+};
+
+// ---------------------------------------------------------------------------
+// fft_core: all passes of one transform for one thread.
+//   in : x[u*R0 + r]  = element  lt + u*T + r*(N/R0)       (first-pass order)
+//   out: x[u*RL + bitrev(r)] = element (j-k)*RL + k + r*NSL, j = lt+u*T, k = j mod NSL
+//        (for the greedy plan NSL = N/RL, so that is  j + r*(N/RL) )
+// buf is this transform's padded shared-memory line (unused when npass == 1).
+// Barriers are CTA-wide: every thread of the CTA must call this the same
+// number of times.  The first barrier protects buf against readers of the
+// previous use (previous transform's last pass).
+// ---------------------------------------------------------------------------
+template <class P, int EPT>
+__device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
+                                         const float2 *__restrict__ tw)
+{
+    constexpr int N = P::N, T = P::T, NPASS = P::npass();
+    static_for<0, NPASS>([&](auto p_) {
+        constexpr int p = decltype(p_)::value;
+        constexpr int R = P::radix(p), NS = P::ns(p), NB = EPT / R;
+        constexpr bool first = (p == 0), last = (p == NPASS - 1);
+        constexpr int STR = N / R;
+        constexpr int LR = ilog2(R);
+
+        if constexpr (!first) {
+#pragma unroll
+            for (int u = 0; u < NB; u++)
+#pragma unroll
+                for (int r = 0; r < R; r++) x[u * R + r] = buf[pad(lt + u * T + r * STR)];
+            if constexpr (!last) __syncthreads();     // all reads before the in-place writes
+        }
+
+        static_for<0, NB>([&](auto u_) {
+            constexpr int u = decltype(u_)::value;
+            if constexpr (!first) {
+                const int k = (lt + u * T) & (NS - 1);
+                const float2 *t = tw + P::tw_offset(p) + k;
+#pragma unroll
+                for (int r = 1; r < R; r++) x[u * R + r] = cmul(x[u * R + r], __ldg(t + (r - 1) * NS));
+            }
+            dft_dif<R, u * R>(x);
+        });
+
+        if constexpr (!last) {
+            if constexpr (first) __syncthreads();
+            static_for<0, NB>([&](auto u_) {
+                constexpr int u = decltype(u_)::value;
+                const int j = lt + u * T;
+                if constexpr (NS == 1 && (R % 2 == 0)) {
+                    // thread-contiguous run of R outputs: 128-bit stores
+                    static_for<0, R / 2>([&](auto q_) {
+                        constexpr int q = decltype(q_)::value;
+                        float2 a = x[u * R + bitrev(2 * q, LR)], b = x[u * R + bitrev(2 * q + 1, LR)];
+                        *reinterpret_cast<float4 *>(buf + pad(j * R + 2 * q)) =
+                            make_float4(a.x, a.y, b.x, b.y);
+                    });
+                } else {
+                    const int k = j & (NS - 1);
+                    const int base = (j - k) * R + k;
+                    static_for<0, R>([&](auto r_) {
+                        constexpr int r = decltype(r_)::value;
+                        buf[pad(base + r * NS)] = x[u * R + bitrev(r, LR)];
+                    });
+                }
+            });
+            __syncthreads();
+        }
+    });
+}
+
+// element index of first-pass register slot e (= u*R0 + r)
+template <class P, int EPT>
+__device__ __forceinline__ constexpr int in_index(int lt, int e)
+{
+    constexpr int R0 = P::radix(0);
+    return lt + (e / R0) * P::T + (e % R0) * (P::N / R0);
+}
+
+// f(natural_index, value) for every output this thread holds after fft_core
+template <class P, int EPT, class F>
+__device__ __forceinline__ void for_each_output(const float2 (&x)[EPT], int lt, F &&f)
+{
+    constexpr int NPASS = P::npass();
+    constexpr int R = P::radix(NPASS - 1), NS = P::ns(NPASS - 1), NB = EPT / R, LR = ilog2(R);
+    static_for<0, NB>([&](auto u_) {
+        constexpr int u = decltype(u_)::value;
+        const int j = lt + u * P::T;
+        const int k = j & (NS - 1);
+        const int base = (j - k) * R + k;
+        static_for<0, R>([&](auto r_) {
+            constexpr int r = decltype(r_)::value;
+            f(base + r * NS, x[u * R + bitrev(r, LR)]);
+        });
+    });
+}
+
+} // namespace fftdev
+} // namespace clb200

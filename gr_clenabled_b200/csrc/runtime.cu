@@ -1,0 +1,171 @@
+// runtime.cu -- device selection, buffers, error state, handle lifetime.
+// Replaces GRCLBase::InitOpenCL / cleanup (lib/GRCLBase.cpp:17-369, :423-483).
+#include "common.cuh"
+#include <cstdarg>
+
+namespace clb200 {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int device_sm_count(int device)
+{
+    static int cache[64];
+    if (device < 0 || device >= 64) return 148;
+    if (cache[device] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+            v <= 0)
+            v = 148;
+        cache[device] = v;
+    }
+    return cache[device];
+}
+
+int Buf::reserve(size_t bytes)
+{
+    if (bytes <= cap) return CLB200_OK;
+    release();
+    size_t want = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = host ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error("%s of %zu bytes failed: %s", host ? "cudaHostAlloc" : "cudaMalloc", want,
+                  cudaGetErrorString(e));
+        cudaGetLastError();
+        return CLB200_ENOMEM;
+    }
+    cap = want;
+    return CLB200_OK;
+}
+
+void Buf::release()
+{
+    if (p) {
+        if (host) cudaFreeHost(p);
+        else cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+} // namespace clb200
+
+using namespace clb200;
+
+int clb200_block::init_slots()
+{
+    if (slots_ready) return CLB200_OK;
+    for (int i = 0; i < NSLOT; i++) {
+        Slot &s = slot[i];
+        for (int k = 0; k < MAXPORT; k++) {
+            s.pin_in[k].host = true;
+            s.pin_out[k].host = true;
+        }
+        CLB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CLB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    slots_ready = true;
+    return CLB200_OK;
+}
+
+clb200_block::~clb200_block()
+{
+    DeviceGuard g(device);
+    for (int i = 0; i < NSLOT; i++) {
+        Slot &s = slot[i];
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        for (int k = 0; k < MAXPORT; k++) {
+            s.pin_in[k].release();
+            s.pin_out[k].release();
+            s.dev_in[k].release();
+            s.dev_out[k].release();
+        }
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+}
+
+extern "C" {
+
+const char *clb200_version(void) { return "clenabled_b200 0.1 (sm_100a)"; }
+
+const char *clb200_last_error(void) { return g_err; }
+
+int clb200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (e != cudaSuccess) {
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return CLB200_ECUDA;
+    }
+    return n;
+}
+
+int clb200_device_name(int device, char *buf, int buflen)
+{
+    CLB_CHECK(buf && buflen > 0, CLB200_EINVAL, "bad buffer");
+    cudaDeviceProp p;
+    CLB_CUDA(cudaGetDeviceProperties(&p, device));
+    snprintf(buf, buflen, "%s (sm_%d%d, %d SMs, %.1f GB)", p.name, p.major, p.minor,
+             p.multiProcessorCount, (double)p.totalGlobalMem / 1e9);
+    return CLB200_OK;
+}
+
+int clb200_device_sm_count(int device) { return device_sm_count(device); }
+
+int clb200_select_device(int platform_type, int dev_selector, int platform_id, int dev_id)
+{
+    (void)platform_id;
+    // OCLTYPE_GPU=1, ACCELERATOR=2, CPU=3, ANY=4 (GRCLBase.h:64-67): there is no
+    // CPU device behind this library; a flowgraph that asks for one gets the GPU.
+    CLB_CHECK(platform_type >= 1 && platform_type <= 4, CLB200_EINVAL,
+              "openCLPlatformType %d is not one of 1..4", platform_type);
+    int n = clb200_device_count();
+    if (n < 0) return n;
+    CLB_CHECK(n > 0, CLB200_ECUDA, "no CUDA device present");
+    int dev = (dev_selector == 2) ? dev_id : 0;   // OCLDEVICESELECTOR_SPECIFIC=2 (GRCLBase.h:69-70)
+    CLB_CHECK(dev >= 0 && dev < n, CLB200_EINVAL, "device %d requested, %d present", dev, n);
+    return dev;
+}
+
+int clb200_destroy(clb200_handle h)
+{
+    if (!h) return CLB200_OK;
+    delete h;
+    return CLB200_OK;
+}
+
+int clb200_get_counters(clb200_handle h, uint64_t *h2d, uint64_t *d2h, uint64_t *launches)
+{
+    CLB_CHECK(h != nullptr, CLB200_EINVAL, "null handle");
+    if (h2d) *h2d = h->n_h2d;
+    if (d2h) *d2h = h->n_d2h;
+    if (launches) *launches = h->n_launch;
+    return CLB200_OK;
+}
+
+} // extern "C"

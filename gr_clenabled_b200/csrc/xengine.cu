@@ -1,0 +1,655 @@
+// xengine.cu -- clXEngine: the X stage of an FX correlator.
+//
+// Reference: CharToComplex (lib/clXEngine_impl.cc:819-916) expands the int8
+// integration buffer to complex float in global memory (4x the bytes), then
+// XCorrelate (:708-817) runs one work-item per (channel, baseline), each
+// streaming 2*T strided global loads with no reuse.
+//
+// Here: for every frequency channel f the integration is the real int8 matrix
+//     Z_f[(input v, re|im)][t]            (2*NV rows, T columns),
+// and all visibilities of the channel come from the Gram matrix G = Z Z^T:
+//     Re V(v1,v2) = G[(v1,re),(v2,re)] + G[(v1,im),(v2,im)]
+//     Im V(v1,v2) = G[(v1,im),(v2,re)] - G[(v1,re),(v2,im)]          (:729-736)
+// computed EXACTLY on the int8 tensor cores (s8 x s8 -> s32).  The input layout
+// [t][station][chan][pol][re,im] has time outermost, the tensor cores want time
+// innermost, so a CTA stages a tile of FC channels x 32 time steps: coalesced
+// 32-bit loads, a 4x4 byte transpose in registers (PRMT), bank-conflict-free
+// stores into a per-channel K-major shared-memory image; one warp then owns one
+// channel (or a share of its row tiles), loads each 16x32 operand fragment ONCE
+// and uses it both as the A operand of its own row tile and as the B operand of
+// every row tile at or below it -- rows are ordered [8 inputs re | 8 inputs im]
+// so that the re/im combination above happens inside one thread's accumulators.
+// Only the lower triangle of 8x8-input blocks is computed.
+// HBM traffic: the int8 input once + the visibilities once (71.4 MB
+// per integration at 32 stations x 1024 channels x 1024 time steps).
+#include "common.cuh"
+#include "fft_device.cuh"      // static_for
+#include <cmath>
+
+using namespace clb200;
+using clb200::fftdev::static_for;
+
+namespace {
+
+constexpr int XE_WARPS = 16;
+constexpr int XE_THREADS = XE_WARPS * 32;
+constexpr int XE_TT = 32;             // time steps per stage = one k32 MMA step
+constexpr int XE_RSW = 12;            // row stride in words: 32 B data + 16 B pad
+
+__device__ __forceinline__ void mma_s8(int (&d)[4], const int (&a)[4], int b0, int b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};\n"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct XeParams {
+    const int8_t *in;       // [t][station][Fstride][npol][2]
+    int32_t *out_i32;       // [F][nbl][npol*npol][2]   (may be null)
+    float2 *out_f32;        // same shape (may be null)
+    int A, npol, F, Fstride, f_off, T;
+    int accumulate;         // out += result
+    int aligned;            // rows are 4-byte aligned -> 32-bit loads
+    float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
+};
+
+// which row tiles warp share Q of WPC owns
+template <int WPC, int Q>
+__host__ __device__ constexpr bool owns(int mi)
+{
+    int r = mi % (2 * WPC);
+    return r == Q || r == 2 * WPC - 1 - Q;
+}
+template <int MT, int WPC, int Q>
+__host__ __device__ constexpr int tile_base(int mi)     // accumulator tiles before row tile mi
+{
+    int n = 0;
+    for (int m = 0; m < mi; m++)
+        if (owns<WPC, Q>(m)) n += m + 1;
+    return n;
+}
+template <int MT, int WPC, int Q>
+__host__ __device__ constexpr int mi_max()
+{
+    int mx = -1;
+    for (int m = 0; m < MT; m++)
+        if (owns<WPC, Q>(m)) mx = m;
+    return mx;
+}
+
+// MT: row tiles (8 inputs each) per channel; WPC: warps sharing one channel; FC = 16/WPC
+template <int MT, int WPC, int Q>
+__device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
+{
+    constexpr int FC = XE_WARPS / WPC;
+    constexpr int NT = tile_base<MT, WPC, Q>(MT);            // accumulator tiles of this warp
+    constexpr int MMAX = mi_max<MT, WPC, Q>();
+    constexpr int CSW = MT * 16 * XE_RSW + 2;                // channel stride (words), = 2 mod 32
+    constexpr int ZW = FC * CSW;                             // words per stage buffer
+    constexpr int NVP = MT * 8;
+    const int npol = p.npol;
+    const int astn = NVP / npol;                             // padded station count
+    const int runw = FC * npol / 2;                          // 32-bit words per (t, station) run
+    const int nquad = 8 * astn * runw;                       // 4-t quads per stage
+    constexpr int QPT = (32 * MT * FC + XE_THREADS - 1) / XE_THREADS;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int chl = warp / WPC;                              // channel within the CTA
+    const int nbl = p.A * (p.A + 1) / 2;
+    const long rowb = (long)p.Fstride * npol * 2;            // bytes per (t, station)
+    const long frameb = rowb * p.A;                          // bytes per t
+    const int ngroups = (p.F + FC - 1) / FC;
+    const int nstage = (p.T + XE_TT - 1) / XE_TT;
+
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int f0 = grp * FC;
+        const int8_t *gbase = p.in + ((long)(p.f_off + f0)) * npol * 2;
+        int acc[NT > 0 ? NT : 1][2][4];
+#pragma unroll
+        for (int i = 0; i < (NT > 0 ? NT : 1); i++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][c][j] = 0;
+
+        uint32_t pre[QPT][4];
+        auto load_stage = [&](int st) {
+#pragma unroll
+            for (int i = 0; i < QPT; i++) {
+                const int e = threadIdx.x + i * XE_THREADS;
+                const int wi = e % runw, r1 = e / runw;
+                const int qlo = r1 & 3, r2 = r1 >> 2;
+                const int s = r2 % astn, qhi = r2 / astn;
+                const int t0 = st * XE_TT + (qhi * 4 + qlo) * 4;
+                // channels covered by this word must exist
+                const int chw = (npol == 1) ? 2 * wi : wi;
+                const bool ok = e < nquad && s < p.A && (f0 + chw) < p.F;
+                const bool ok2 = (npol == 1) ? (f0 + chw + 1) < p.F : true;
+                const int8_t *src = gbase + (long)t0 * frameb + (long)s * rowb + wi * 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t w = 0;
+                    if (ok && (t0 + k) < p.T) {
+                        const int8_t *q = src + (long)k * frameb;
+                        if (p.aligned && ok2) {
+                            w = __ldg(reinterpret_cast<const unsigned int *>(q));
+                        } else {
+                            w = (uint32_t)(uint8_t)q[0] | ((uint32_t)(uint8_t)q[1] << 8);
+                            if (ok2) w |= ((uint32_t)(uint8_t)q[2] << 16) | ((uint32_t)(uint8_t)q[3] << 24);
+                        }
+                    }
+                    pre[i][k] = w;
+                }
+            }
+        };
+        auto store_stage = [&](uint32_t *z) {
+#pragma unroll
+            for (int i = 0; i < QPT; i++) {
+                const int e = threadIdx.x + i * XE_THREADS;
+                if (e >= nquad) continue;
+                const int wi = e % runw, r1 = e / runw;
+                const int qlo = r1 & 3, r2 = r1 >> 2;
+                const int s = r2 % astn, qhi = r2 / astn;
+                const int q = qhi * 4 + qlo;
+                // 4x4 byte transpose: o[b] = byte b of the four time steps
+                const uint32_t lo01 = __byte_perm(pre[i][0], pre[i][1], 0x5140);
+                const uint32_t hi01 = __byte_perm(pre[i][0], pre[i][1], 0x7362);
+                const uint32_t lo23 = __byte_perm(pre[i][2], pre[i][3], 0x5140);
+                const uint32_t hi23 = __byte_perm(pre[i][2], pre[i][3], 0x7362);
+                const uint32_t o0 = __byte_perm(lo01, lo23, 0x5410);
+                const uint32_t o1 = __byte_perm(lo01, lo23, 0x7632);
+                const uint32_t o2 = __byte_perm(hi01, hi23, 0x5410);
+                const uint32_t o3 = __byte_perm(hi01, hi23, 0x7632);
+                int ch_a, ch_b, v_a, v_b;
+                if (npol == 1) {            // word = channels 2wi, 2wi+1 of input s
+                    ch_a = 2 * wi; ch_b = 2 * wi + 1; v_a = s; v_b = s;
+                } else {                    // word = channel wi, pol X and Y of station s
+                    ch_a = wi; ch_b = wi; v_a = 2 * s; v_b = 2 * s + 1;
+                }
+                const int ra = ((v_a >> 3) * 16 + (v_a & 7)) * XE_RSW;
+                const int rb = ((v_b >> 3) * 16 + (v_b & 7)) * XE_RSW;
+                z[ch_a * CSW + ra + q] = o0;                       // (re)
+                z[ch_a * CSW + ra + 8 * XE_RSW + q] = o1;          // (im)
+                z[ch_b * CSW + rb + q] = o2;
+                z[ch_b * CSW + rb + 8 * XE_RSW + q] = o3;
+            }
+        };
+
+        __syncthreads();        // previous group's readers are done with zbuf
+        load_stage(0);
+        store_stage(zbuf);
+        if (nstage > 1) load_stage(1);
+        __syncthreads();
+
+        for (int st = 0; st < nstage; st++) {
+            const uint32_t *z = zbuf + (st & 1) * ZW + chl * CSW;
+            if constexpr (NT > 0) {
+                int a[MMAX + 1][4];
+#pragma unroll
+                for (int m = 0; m <= MMAX; m++) {
+                    const uint32_t *r = z + (m * 16 + g) * XE_RSW + tig;
+                    a[m][0] = (int)r[0];
+                    a[m][1] = (int)r[8 * XE_RSW];
+                    a[m][2] = (int)r[4];
+                    a[m][3] = (int)r[8 * XE_RSW + 4];
+                }
+                static_for<0, MT>([&](auto mi_) {
+                    constexpr int mi = decltype(mi_)::value;
+                    if constexpr (owns<WPC, Q>(mi)) {
+                        constexpr int tb = tile_base<MT, WPC, Q>(mi);
+                        static_for<0, mi + 1>([&](auto nj_) {
+                            constexpr int nj = decltype(nj_)::value;
+                            mma_s8(acc[tb + nj][0], a[mi], a[nj][0], a[nj][2]);   // columns = re rows of tile nj
+                            mma_s8(acc[tb + nj][1], a[mi], a[nj][1], a[nj][3]);   // columns = im rows
+                        });
+                    }
+                });
+            }
+            if (st + 1 < nstage) {
+                store_stage(zbuf + ((st + 1) & 1) * ZW);
+                if (st + 2 < nstage) load_stage(st + 2);
+            }
+            __syncthreads();
+        }
+
+        // ---- epilogue: combine re/im products, scatter the lower triangle ----
+        const int f = f0 + chl;
+        if constexpr (NT > 0) {
+            if (f < p.F) {
+                static_for<0, MT>([&](auto mi_) {
+                    constexpr int mi = decltype(mi_)::value;
+                    if constexpr (owns<WPC, Q>(mi)) {
+                        constexpr int tb = tile_base<MT, WPC, Q>(mi);
+                        static_for<0, mi + 1>([&](auto nj_) {
+                            constexpr int nj = decltype(nj_)::value;
+                            const int (&C)[4] = acc[tb + nj][0];
+                            const int (&D)[4] = acc[tb + nj][1];
+                            const int v1 = mi * 8 + g;
+#pragma unroll
+                            for (int h = 0; h < 2; h++) {
+                                const int v2 = nj * 8 + 2 * tig + h;
+                                const int re = C[h] + D[2 + h];
+                                const int im = C[2 + h] - D[h];
+                                const int s1 = v1 / npol, p1 = v1 % npol;
+                                const int s2 = v2 / npol, p2 = v2 % npol;
+                                if (s1 < p.A && s2 <= s1) {
+                                    const long k = (long)s1 * (s1 + 1) / 2 + s2;
+                                    const long o = (((long)f * nbl + k) * npol + p1) * npol + p2;
+                                    if (p.out_i32) {
+                                        int2 v = make_int2(re, im);
+                                        if (p.accumulate) {
+                                            int2 old = reinterpret_cast<int2 *>(p.out_i32)[o];
+                                            v.x += old.x;
+                                            v.y += old.y;
+                                        }
+                                        reinterpret_cast<int2 *>(p.out_i32)[o] = v;
+                                    }
+                                    if (p.out_f32) {
+                                        float2 v = make_float2((float)re * p.scale, (float)im * p.scale);
+                                        if (p.accumulate) {
+                                            float2 old = p.out_f32[o];
+                                            v.x += old.x;
+                                            v.y += old.y;
+                                        }
+                                        p.out_f32[o] = v;
+                                    }
+                                }
+                            }
+                        });
+                    }
+                });
+            }
+        }
+    }
+}
+
+template <int MT, int WPC>
+__global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_i8(XeParams p)
+{
+    extern __shared__ __align__(16) uint32_t xe_smem[];
+    if constexpr (WPC == 1) {
+        xe_body<MT, 1, 0>(p, xe_smem);
+    } else {
+        // every warp share runs the same barrier sequence; only the tile sets differ
+        const int q = (threadIdx.x >> 5) % WPC;
+        static_for<0, WPC>([&](auto q_) {
+            constexpr int Q = decltype(q_)::value;
+            if (q == Q) xe_body<MT, WPC, Q>(p, xe_smem);
+        });
+    }
+}
+
+// packed 4-bit (hi nibble re, lo nibble im) -> int8 pairs; LUT of CharToComplex (:833)
+__global__ void k_unpack4(const uint8_t *__restrict__ in, int8_t *__restrict__ out, long n)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int b = in[i];
+        int hi = b >> 4, lo = b & 15;
+        hi = hi < 8 ? hi : (hi == 8 ? 0 : hi - 16);
+        lo = lo < 8 ? lo : (lo == 8 ? 0 : lo - 16);
+        reinterpret_cast<char2 *>(out)[i] = make_char2((char)hi, (char)lo);
+    }
+}
+
+// complex-float input: one thread per (channel, baseline, pol pair); the float
+// accumulation runs in t order like the reference work-item (:739-810)
+__global__ void k_xengine_c32(const float2 *__restrict__ in, float2 *__restrict__ out, int A,
+                              int npol, int F, int Fstride, int f_off, int T, int accumulate)
+{
+    const int nbl = A * (A + 1) / 2;
+    const long total = (long)F * nbl * npol * npol;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long frame = (long)A * Fstride * npol;
+    for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+        const int pp = (int)(o % (npol * npol));
+        const long fk = o / (npol * npol);
+        const int k = (int)(fk % nbl), f = (int)(fk / nbl);
+        int s1 = (int)(-0.5 + sqrt(0.25 + 2.0 * k));
+        while ((s1 + 1) * (s1 + 2) / 2 <= k) s1++;
+        while (s1 * (s1 + 1) / 2 > k) s1--;
+        const int s2 = k - s1 * (s1 + 1) / 2;
+        const int p1 = pp / npol, p2 = pp % npol;
+        const float2 *r = in + ((long)s1 * Fstride + f_off + f) * npol + p1;
+        const float2 *c = in + ((long)s2 * Fstride + f_off + f) * npol + p2;
+        float re = 0.f, im = 0.f;
+        for (int t = 0; t < T; t++) {
+            const float2 a = __ldg(r + t * frame), b = __ldg(c + t * frame);
+            re += a.x * b.x + a.y * b.y;
+            im += a.y * b.x - a.x * b.y;
+        }
+        if (accumulate) {
+            re += out[o].x;
+            im += out[o].y;
+        }
+        out[o] = make_float2(re, im);
+    }
+}
+
+__global__ void k_i32_to_f32(const int2 *__restrict__ in, float2 *__restrict__ out, long n,
+                             float scale, int accumulate)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float2 v = make_float2((float)in[i].x * scale, (float)in[i].y * scale);
+        if (accumulate) {
+            v.x += out[i].x;
+            v.y += out[i].y;
+        }
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------- host --
+typedef void (*xe_kernel_t)(XeParams);
+struct XeVariant {
+    int mt, wpc, fc, smem_bytes;
+    xe_kernel_t kernel;
+};
+template <int MT, int WPC>
+XeVariant make_xe()
+{
+    constexpr int FC = XE_WARPS / WPC;
+    constexpr int CSW = MT * 16 * XE_RSW + 2;
+    return XeVariant{MT, WPC, FC, 2 * FC * CSW * 4, &k_xengine_i8<MT, WPC>};
+}
+const XeVariant *pick_xe(int nv)
+{
+    static const XeVariant tab[] = {
+        make_xe<1, 1>(), make_xe<2, 1>(), make_xe<3, 1>(), make_xe<4, 1>(),
+        make_xe<5, 2>(), make_xe<6, 2>(), make_xe<7, 2>(), make_xe<8, 4>(),
+    };
+    int mt = (nv + 7) / 8;
+    if (mt < 1 || mt > 8) return nullptr;
+    return &tab[mt - 1];
+}
+
+struct XEngine : clb200_block {
+    int data_type = 0, npol = 1, A = 0, F = 0, T = 0;
+    int Ftotal = 0, f_first = 0;       // channel shard within the caller's buffer
+    const XeVariant *var = nullptr;
+    Buf d_in[2], d_unpacked, d_acc, d_out;
+    Buf pin_in[2], pin_out;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
+    long nbl() const { return (long)A * (A + 1) / 2; }
+    long out_items() const { return (long)F * nbl() * npol * npol; }
+    size_t sample_bytes() const
+    {
+        return data_type == CLB200_DTYPE_COMPLEX ? 8 : (data_type == CLB200_DTYPE_BYTE ? 2 : 1);
+    }
+    ~XEngine() override
+    {
+        DeviceGuard g(device);
+        if (s_copy) cudaStreamSynchronize(s_copy);
+        if (s_comp) cudaStreamSynchronize(s_comp);
+        for (int i = 0; i < 2; i++) {
+            d_in[i].release();
+            pin_in[i].release();
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+        }
+        d_unpacked.release();
+        d_acc.release();
+        d_out.release();
+        pin_out.release();
+        if (ev_done) cudaEventDestroy(ev_done);
+        if (s_copy) cudaStreamDestroy(s_copy);
+        if (s_comp) cudaStreamDestroy(s_comp);
+    }
+};
+
+// enqueue the correlation of `T` time steps held at d_in (layout [t][A][Fstride][npol]);
+// exactly one of out_i32 / out_f32 may be null
+int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32_t *out_i32,
+              float2 *out_f32, int accumulate, cudaStream_t st)
+{
+    const int sms = device_sm_count(x->device);
+    if (x->data_type == CLB200_DTYPE_COMPLEX) {
+        CLB_CHECK(out_f32 != nullptr, CLB200_EINVAL, "clXEngine: complex input has no integer output");
+        long total = x->out_items();
+        k_xengine_c32<<<grid_for((total + 127) / 128, sms, 16), 128, 0, st>>>(
+            (const float2 *)d_in, out_f32, x->A, x->npol, x->F, Fstride, f_off, T, accumulate);
+        CLB_CUDA(cudaGetLastError());
+        x->n_launch++;
+        return CLB200_OK;
+    }
+    const int8_t *src = (const int8_t *)d_in;
+    float scale = 1.0f / (127.0f * 127.0f);
+    if (x->data_type == CLB200_DTYPE_PACKEDXY) {
+        long n = (long)T * x->A * Fstride * x->npol;
+        CLB_TRY(x->d_unpacked.reserve((size_t)n * 2));
+        k_unpack4<<<grid_for((n + 255) / 256, sms, 8), 256, 0, st>>>((const uint8_t *)d_in,
+                                                                     (int8_t *)x->d_unpacked.p, n);
+        CLB_CUDA(cudaGetLastError());
+        x->n_launch++;
+        src = (const int8_t *)x->d_unpacked.p;
+        scale = 1.0f / 49.0f;
+    }
+    XeParams p;
+    p.in = src;
+    p.out_i32 = out_i32;
+    p.out_f32 = out_f32;
+    p.A = x->A;
+    p.npol = x->npol;
+    p.F = x->F;
+    p.Fstride = Fstride;
+    p.f_off = f_off;
+    p.T = T;
+    p.accumulate = accumulate;
+    p.scale = scale;
+    long rowb = (long)Fstride * x->npol * 2;
+    p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
+    const XeVariant *v = x->var;
+    int ngroups = (x->F + v->fc - 1) / v->fc;
+    v->kernel<<<grid_for(ngroups, sms, 1), XE_THREADS, v->smem_bytes, st>>>(p);
+    CLB_CUDA(cudaGetLastError());
+    x->n_launch++;
+    return CLB200_OK;
+}
+
+int xe_init_streams(XEngine *x)
+{
+    if (x->s_copy) return CLB200_OK;
+    CLB_CUDA(cudaStreamCreateWithFlags(&x->s_copy, cudaStreamNonBlocking));
+    CLB_CUDA(cudaStreamCreateWithFlags(&x->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CLB_CUDA(cudaEventCreateWithFlags(&x->ev_in[i], cudaEventDisableTiming));
+        CLB_CUDA(cudaEventCreateWithFlags(&x->ev_free[i], cudaEventDisableTiming));
+        x->pin_in[i].host = true;
+    }
+    x->pin_out.host = true;
+    CLB_CUDA(cudaEventCreateWithFlags(&x->ev_done, cudaEventDisableTiming));
+    return CLB200_OK;
+}
+
+// host-buffer integration: time-chunked H2D on one stream overlapped with the
+// correlation of the previous chunk on another; int32 partial sums stay on the device
+int xe_work(XEngine *x, const void *in, void *out, bool want_i32, int accumulate)
+{
+    CLB_TRY(xe_init_streams(x));
+    const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
+    const size_t sb = x->sample_bytes();
+    const size_t width = (size_t)x->F * x->npol * sb;             // bytes of this shard per (t, station)
+    const size_t pitch = (size_t)Ftot * x->npol * sb;
+    const long rows_per_t = x->A;
+    const bool is_int = x->data_type != CLB200_DTYPE_COMPLEX;
+    CLB_CHECK(!(want_i32 && !is_int), CLB200_EINVAL, "clXEngine: complex input has no integer output");
+    const long nout = x->out_items();
+    const bool pinned = is_pinned(in);
+    // chunk: about 8 MiB of input, a multiple of the 32-step stage
+    long tch = std::max<long>(XE_TT, ((long)(8 << 20) / std::max<size_t>(1, width * rows_per_t)) / XE_TT * XE_TT);
+    tch = std::min<long>(tch, x->T);
+    if (is_int) CLB_TRY(x->d_acc.reserve((size_t)nout * 8));
+    CLB_TRY(x->d_out.reserve((size_t)nout * 8));
+    int c = 0;
+    for (long t0 = 0; t0 < x->T; t0 += tch, c++) {
+        const long nt = std::min<long>(tch, x->T - t0);
+        const int b = c & 1;
+        CLB_TRY(x->d_in[b].reserve(width * rows_per_t * tch));
+        if (c >= 2) CLB_CUDA(cudaStreamWaitEvent(x->s_copy, x->ev_free[b], 0));
+        const char *src = (const char *)in + (size_t)t0 * rows_per_t * pitch + (size_t)x->f_first * x->npol * sb;
+        if (!pinned) {
+            // stage through pinned memory (only the shard's columns)
+            if (c >= 2) CLB_CUDA(cudaEventSynchronize(x->ev_in[b]));
+            CLB_TRY(x->pin_in[b].reserve(width * rows_per_t * tch));
+            for (long r = 0; r < nt * rows_per_t; r++)
+                memcpy((char *)x->pin_in[b].p + r * width, src + r * pitch, width);
+            CLB_CUDA(cudaMemcpyAsync(x->d_in[b].p, x->pin_in[b].p, width * rows_per_t * nt,
+                                     cudaMemcpyHostToDevice, x->s_copy));
+        } else {
+            CLB_CUDA(cudaMemcpy2DAsync(x->d_in[b].p, width, src, pitch, width, nt * rows_per_t,
+                                       cudaMemcpyHostToDevice, x->s_copy));
+        }
+        x->n_h2d += width * rows_per_t * nt;
+        CLB_CUDA(cudaEventRecord(x->ev_in[b], x->s_copy));
+        CLB_CUDA(cudaStreamWaitEvent(x->s_comp, x->ev_in[b], 0));
+        if (is_int)
+            CLB_TRY(xe_launch(x, x->d_in[b].p, (int)nt, x->F, 0, (int32_t *)x->d_acc.p, nullptr, c > 0,
+                              x->s_comp));
+        else
+            CLB_TRY(xe_launch(x, x->d_in[b].p, (int)nt, x->F, 0, nullptr, (float2 *)x->d_out.p,
+                              (c > 0) || accumulate, x->s_comp));
+        CLB_CUDA(cudaEventRecord(x->ev_free[b], x->s_comp));
+    }
+    const void *res = x->d_out.p;
+    if (is_int) {
+        if (want_i32) {
+            res = x->d_acc.p;
+        } else {
+            float scale = x->data_type == CLB200_DTYPE_PACKEDXY ? 1.0f / 49.0f : 1.0f / (127.0f * 127.0f);
+            k_i32_to_f32<<<grid_for((nout + 255) / 256, device_sm_count(x->device), 8), 256, 0, x->s_comp>>>(
+                (const int2 *)x->d_acc.p, (float2 *)x->d_out.p, nout, scale, accumulate);
+            CLB_CUDA(cudaGetLastError());
+            x->n_launch++;
+        }
+    }
+    if (is_pinned(out)) {
+        CLB_CUDA(cudaMemcpyAsync(out, res, (size_t)nout * 8, cudaMemcpyDeviceToHost, x->s_comp));
+        CLB_CUDA(cudaStreamSynchronize(x->s_comp));
+    } else {
+        CLB_TRY(x->pin_out.reserve((size_t)nout * 8));
+        CLB_CUDA(cudaMemcpyAsync(x->pin_out.p, res, (size_t)nout * 8, cudaMemcpyDeviceToHost, x->s_comp));
+        CLB_CUDA(cudaStreamSynchronize(x->s_comp));
+        memcpy(out, x->pin_out.p, (size_t)nout * 8);
+    }
+    x->n_d2h += (size_t)nout * 8;
+    return CLB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, int num_channels,
+                          int integration, clb200_handle *out)
+{
+    CLB_CHECK(out != nullptr, CLB200_EINVAL, "null out");
+    // lib/clXEngine_impl.cc:106-109 throws std::out_of_range for fewer than 2 inputs
+    CLB_CHECK(num_inputs >= 2, CLB200_EINVAL, "clXEngine: Please specify at least 2 inputs (got %d)", num_inputs);
+    CLB_CHECK(npol == 1 || npol == 2, CLB200_EINVAL, "clXEngine: polarization must be 1 or 2, got %d", npol);
+    CLB_CHECK(data_type == CLB200_DTYPE_COMPLEX || data_type == CLB200_DTYPE_BYTE ||
+                  data_type == CLB200_DTYPE_PACKEDXY,
+              CLB200_EINVAL, "clXEngine: data type %d is not complex(1), byte(4) or packed-XY(6)", data_type);
+    CLB_CHECK(num_channels >= 1 && integration >= 1, CLB200_EINVAL,
+              "clXEngine: num_channels and integration must be positive");
+    CLB_CHECK(num_inputs * npol <= 64, CLB200_EINVAL,
+              "clXEngine: %d inputs x %d polarisations exceeds the 64 rows this build tiles for",
+              num_inputs, npol);
+    int n = clb200_device_count();
+    CLB_CHECK(n > 0, CLB200_ECUDA, "no CUDA device present");
+    CLB_CHECK(device >= 0 && device < n, CLB200_EINVAL, "device %d out of range", device);
+    DeviceGuard g(device);
+    XEngine *x = new XEngine;
+    x->kind = KIND_XENGINE;
+    x->device = device;
+    x->data_type = data_type;
+    x->npol = npol;
+    x->A = num_inputs;
+    x->F = num_channels;
+    x->T = integration;
+    x->var = pick_xe(num_inputs * npol);
+    cudaError_t e = cudaFuncSetAttribute((const void *)x->var->kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         x->var->smem_bytes);
+    if (e != cudaSuccess) {
+        set_error("clXEngine: cannot reserve %d B of shared memory: %s", x->var->smem_bytes,
+                  cudaGetErrorString(e));
+        delete x;
+        return CLB200_ECUDA;
+    }
+    *out = x;
+    return CLB200_OK;
+}
+
+long clb200_xengine_input_bytes(clb200_handle h)
+{
+    XEngine *x;
+    if (check_kind(h, KIND_XENGINE, &x) != CLB200_OK) return CLB200_EINVAL;
+    const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
+    return (long)x->T * x->A * Ftot * x->npol * (long)x->sample_bytes();
+}
+
+long clb200_xengine_output_items(clb200_handle h)
+{
+    XEngine *x;
+    if (check_kind(h, KIND_XENGINE, &x) != CLB200_OK) return CLB200_EINVAL;
+    return x->out_items();
+}
+
+int clb200_xengine_set_shard(clb200_handle h, int total_channels, int chan_first)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(chan_first >= 0 && chan_first + x->F <= total_channels, CLB200_EINVAL,
+              "clXEngine: shard [%d, %d) does not fit %d channels", chan_first, chan_first + x->F,
+              total_channels);
+    x->Ftotal = total_channels;
+    x->f_first = chan_first;
+    return CLB200_OK;
+}
+
+int clb200_xengine_work(clb200_handle h, const void *in, void *out_c32, int accumulate)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(in && out_c32, CLB200_EINVAL, "null buffer");
+    DeviceGuard g(x->device);
+    return xe_work(x, in, out_c32, false, accumulate);
+}
+
+int clb200_xengine_work_i32(clb200_handle h, const void *in, int32_t *out_i32)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(in && out_i32, CLB200_EINVAL, "null buffer");
+    DeviceGuard g(x->device);
+    return xe_work(x, in, out_i32, true, 0);
+}
+
+int clb200_xengine_launch_device(clb200_handle h, const void *d_in, void *d_out_c32, int accumulate,
+                                 void *stream)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    DeviceGuard g(x->device);
+    const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
+    return xe_launch(x, d_in, x->T, Ftot, x->f_first, nullptr, (float2 *)d_out_c32, accumulate,
+                     (cudaStream_t)stream);
+}
+
+int clb200_xengine_launch_device_i32(clb200_handle h, const void *d_in, int32_t *d_out_i32, void *stream)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(x->data_type != CLB200_DTYPE_COMPLEX, CLB200_EINVAL,
+              "clXEngine: complex input has no integer output");
+    DeviceGuard g(x->device);
+    const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
+    return xe_launch(x, d_in, x->T, Ftot, x->f_first, d_out_i32, nullptr, 0, (cudaStream_t)stream);
+}
+
+} // extern "C"

@@ -1,0 +1,215 @@
+/*
+ * clenabled_b200.h -- C ABI of libclenabled_b200.so
+ *
+ * The drop-in boundary of the B200-native gr-clenabled hot path.  Everything
+ * above this header (the gr::clenabled::* block classes in
+ * gr_clenabled_b200/host/, the ctypes binding in gr_clenabled_b200/capi.py, a
+ * maintainer's own GNU Radio build) talks to the CUDA kernels only through
+ * these entry points: plain pointers and sizes, opaque handles, int status.
+ * No torch / GNU Radio / C++ types cross it.
+ *
+ * Every entry point cites the reference interface it replaces
+ * (paths relative to the gr-clenabled tree).
+ *
+ * Conventions
+ *   - return 0 on success, <0 on error (CLB200_E*); the message of the last
+ *     error raised on the calling thread is clb200_last_error().
+ *   - "work" calls take HOST pointers (pageable or pinned), copy through the
+ *     handle's pinned rings on the handle's own CUDA streams, and are complete
+ *     (outputs written) when they return -- the contract of gr::block::work().
+ *   - "launch_device" calls take DEVICE pointers and a cudaStream_t (as
+ *     void*), enqueue the same kernels and return without synchronising.  They
+ *     are what a device-resident pipeline (and the roofline bench) uses.
+ *   - a handle is not re-entrant for work(); setters are mutex-guarded and may
+ *     be called from another thread (reference: d_mutex / d_setlock).
+ *   - gr_complex == interleaved {float re, im} (include/clenabled/clSComplex.h:12-17).
+ */
+#ifndef CLENABLED_B200_H
+#define CLENABLED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CLB200_API __attribute__((visibility("default")))
+#else
+#define CLB200_API
+#endif
+
+/* status codes */
+#define CLB200_OK        0
+#define CLB200_EINVAL   -1   /* bad argument (the reference throws in the ctor) */
+#define CLB200_ECUDA    -2   /* CUDA runtime error (the reference prints + exit(0), GRCLBase.cpp:239-257) */
+#define CLB200_ENOMEM   -3
+#define CLB200_ESTATE   -4   /* call not valid in the handle's current state */
+
+/* data types: include/clenabled/GRCLBase.h:57-62 */
+#define CLB200_DTYPE_COMPLEX   1
+#define CLB200_DTYPE_FLOAT     2
+#define CLB200_DTYPE_INT       3
+#define CLB200_DTYPE_BYTE      4   /* clXEngine IChar: interleaved int8 re,im */
+#define CLB200_DTYPE_PACKEDXY  6   /* clXEngine packed 4-bit */
+
+/* operator codes: include/clenabled/clMathOpTypes.h:11-20 */
+#define CLB200_OP_MULTIPLY       1
+#define CLB200_OP_ADD            2
+#define CLB200_OP_SUBTRACT       3
+#define CLB200_OP_COMPLEX_CONJ   4
+#define CLB200_OP_MULTIPLY_CONJ  5
+#define CLB200_OP_EMPTY        255
+#define CLB200_OP_EMPTY_W_COPY 254
+
+/* FFT direction: clFFT's CLFFT_FORWARD=-1 / CLFFT_BACKWARD=+1 (grc/clenabled_clFFT.block.yml:37-41) */
+#define CLB200_FFT_FORWARD  (-1)
+#define CLB200_FFT_BACKWARD (1)
+
+/* secondary element-wise kernels */
+#define CLB200_UNARY_LOG10            1  /* clLog           lib/clLog_impl.cc:139-148 */
+#define CLB200_UNARY_COMPLEX_TO_MAG   2  /* clComplexToMag  lib/clComplexToMag_impl.cc:140-148 */
+#define CLB200_UNARY_COMPLEX_TO_ARG   3  /* clComplexToArg  lib/clComplexToArg_impl.cc:139-151 */
+
+typedef struct clb200_block *clb200_handle;
+
+/* ---------------------------------------------------------------- runtime -- */
+/* replaces GRCLBase::InitOpenCL device discovery (lib/GRCLBase.cpp:17-369)     */
+CLB200_API const char *clb200_version(void);
+CLB200_API const char *clb200_last_error(void);
+CLB200_API int clb200_device_count(void);                 /* <0 on error, 0 = no GPU */
+CLB200_API int clb200_device_name(int device, char *buf, int buflen);
+CLB200_API int clb200_device_sm_count(int device);
+/* (openCLPlatformType, devSelector, platformId, devId) -> CUDA ordinal
+ * (GRCLBase.h:64-70, GRCLBase.cpp:115-188): devId when devSelector==2 else 0 */
+CLB200_API int clb200_select_device(int platform_type, int dev_selector, int platform_id, int dev_id);
+CLB200_API int clb200_destroy(clb200_handle h);           /* any handle; GRCLBase::cleanup/stop */
+/* counters since creation: bytes H2D, bytes D2H, kernel launches */
+CLB200_API int clb200_get_counters(clb200_handle h, uint64_t *h2d, uint64_t *d2h, uint64_t *launches);
+
+/* ------------------------------------------------------------ clMathConst -- */
+/* clMathConst::make(idataType,..,fValue,operatorType,..) include/clenabled/clMathConst.h:51
+ * work: clMathConst_impl::processOpenCL lib/clMathConst_impl.cc:311-361            */
+CLB200_API int clb200_mathconst_create(int dtype, int device, float k, int op, clb200_handle *out);
+CLB200_API int clb200_mathconst_set_k(clb200_handle h, float k);    /* clMathConst.h:54 */
+CLB200_API float clb200_mathconst_k(clb200_handle h);               /* clMathConst.h:53 */
+CLB200_API int clb200_mathconst_work(clb200_handle h, const void *in, void *out, long nitems);
+CLB200_API int clb200_mathconst_launch_device(clb200_handle h, const void *d_in, void *d_out,
+                                              long nitems, void *stream);
+
+/* --------------------------------------------------------------- clMathOp -- */
+/* clMathOp::make(idataType,..,operatorType,..) include/clenabled/clMathOp.h:42
+ * work: clMathOp_impl::processOpenCL lib/clMathOp_impl.cc:361-442                  */
+CLB200_API int clb200_mathop_create(int dtype, int device, int op, clb200_handle *out);
+CLB200_API int clb200_mathop_work(clb200_handle h, const void *a, const void *b, void *c, long nitems);
+CLB200_API int clb200_mathop_launch_device(clb200_handle h, const void *d_a, const void *d_b,
+                                           void *d_c, long nitems, void *stream);
+
+/* --------------------------------------- secondary element-wise (row M5) -- */
+/* clLog::make(..,nValue,kValue) / clComplexToMag / clComplexToArg: 1 in -> 1 out */
+CLB200_API int clb200_unary_create(int kind, int device, float n_value, float k_value,
+                                   clb200_handle *out);
+CLB200_API int clb200_unary_work(clb200_handle h, const void *in, void *out, long nitems);
+CLB200_API int clb200_unary_launch_device(clb200_handle h, const void *d_in, void *d_out,
+                                          long nitems, void *stream);
+/* clSNR (lib/clSNR_impl.cc:105-113): c = fabs(n*log10(a/b)+k), 2 float in -> 1 float out */
+CLB200_API int clb200_snr_create(int device, float n_value, float k_value, clb200_handle *out);
+CLB200_API int clb200_snr_work(clb200_handle h, const float *a, const float *b, float *c, long nitems);
+/* clComplexToMagPhase (lib/clComplexToMagPhase_impl.cc:151-165): 1 complex in -> mag, phase */
+CLB200_API int clb200_c2magphase_create(int device, clb200_handle *out);
+CLB200_API int clb200_c2magphase_work(clb200_handle h, const void *in, float *mag, float *phase,
+                                      long nitems);
+/* clMagPhaseToComplex (lib/clMagPhaseToComplex_impl.cc:169-192): mag, phase -> complex */
+CLB200_API int clb200_magphase2c_create(int device, clb200_handle *out);
+CLB200_API int clb200_magphase2c_work(clb200_handle h, const float *mag, const float *phase,
+                                      void *out, long nitems);
+
+/* ------------------------------------------------------------------ clFFT -- */
+/* clFFT::make(fftSize, clFFTDir, window, idataType, .., num_streams, shift)
+ *   (argument order of lib/clFFT_impl.cc:35-36); ctor lib/clFFT_impl.cc:65-151:
+ *   window_len must be 0 or fft_size (:74-76 throws).
+ * dtype COMPLEX: c32[fft_size] -> c32[fft_size] per item; dtype FLOAT (forward
+ * only): f32[fft_size] -> full Hermitian c32[fft_size] spectrum (:556-565,608-630).
+ * Unnormalised in both directions (:121-122).  shift: forward swaps the output
+ * halves (:594-607), backward swaps the input halves (:548-553).
+ * fft_size: power of two, 2 .. 16384.                                             */
+CLB200_API int clb200_fft_create(int fft_size, int dir, const float *window, int window_len,
+                                 int dtype, int device, int shift, clb200_handle *out);
+/* processOpenCL (lib/clFFT_impl.cc:526-634): nvec items (vectors) of one stream   */
+CLB200_API int clb200_fft_work(clb200_handle h, const void *in, void *out, long nvec);
+/* the num_streams loop (:537): stream s reads in[s], writes out[s]              */
+CLB200_API int clb200_fft_work_streams(clb200_handle h, const void *const *in, void *const *out,
+                                       int nstreams, long nvec);
+CLB200_API int clb200_fft_launch_device(clb200_handle h, const void *d_in, void *d_out, long nvec,
+                                        void *stream);
+
+/* --------------------------------------------------------------- clFilter -- */
+/* clFilter::make(..,decimation,taps,nthreads,setDebug,use_time) include/clenabled/clFilter.h:52-53
+ * use_time=1: td_FIR_complex (lib/clFilter_impl.cc:162-194, :505-589)
+ * use_time=0: FFT filter, fft_filter_ccf sizes (lib/fft_filter.cc:72-97), lib/clFilter_impl.cc:592-681
+ * Streaming semantics: y[n] = sum_k taps[k] x[n-k] over the whole stream fed so
+ * far (zero initial state); the last ntaps-1 inputs and the decimation phase are
+ * kept device-resident between calls, so any chunking gives the same stream.    */
+CLB200_API int clb200_filter_create(int device, int decimation, const float *taps, int ntaps,
+                                    int use_time, clb200_handle *out);
+/* set_taps2 (clFilter.h:55): takes effect on the next work(); history is reset
+ * (lib/clFilter_impl.cc:774-789)                                                */
+CLB200_API int clb200_filter_set_taps(clb200_handle h, const float *taps, int ntaps);
+CLB200_API int clb200_filter_ntaps(clb200_handle h);
+CLB200_API int clb200_filter_get_taps(clb200_handle h, float *taps, int cap);   /* clFilter.h:56 */
+CLB200_API int clb200_filter_reset(clb200_handle h);
+/* fft_filter_ccf::compute_sizes result the reference would use (fft_filter.cc:77-78) */
+CLB200_API int clb200_filter_ref_sizes(int ntaps, int *fftsize, int *nsamples);
+/* consumes n_in samples, writes *n_out = number of decimated outputs produced    */
+CLB200_API int clb200_filter_work(clb200_handle h, const void *in, long n_in, void *out,
+                                  long *n_out);
+/* device pointers; d_in holds n_in NEW samples (history is inside the handle)   */
+CLB200_API int clb200_filter_launch_device(clb200_handle h, const void *d_in, long n_in,
+                                           void *d_out, long *n_out, void *stream);
+
+/* ------------------------------------------------- clPolyphaseChannelizer -- */
+/* clPolyphaseChannelizer::make(..,taps,buf_items,num_channels,ninputs_per_iter,ch_map,..)
+ *   include/clenabled/clPolyphaseChannelizer.h:48-49; ctor checks lib/..._impl.cc:59-62
+ * general_work lib/clPolyphaseChannelizer_impl.cc:83-109, kernels :156-177, plan :208-225.
+ * in: GNU Radio history layout -- in[0] is ntaps-1 samples in the past; the call
+ * reads (niter-1)*R + ntaps samples and writes niter*nmap outputs.              */
+CLB200_API int clb200_pfb_create(int device, const float *taps, int ntaps, int buf_items,
+                                 int num_channels, int ninputs_per_iter, const int *ch_map,
+                                 int nmap, clb200_handle *out);
+CLB200_API int clb200_pfb_work(clb200_handle h, const void *in, void *out, long niter);
+CLB200_API int clb200_pfb_launch_device(clb200_handle h, const void *d_in, void *d_out, long niter,
+                                        void *stream);
+
+/* -------------------------------------------------------------- clXEngine -- */
+/* clXEngine::make(.. data_type, polarization, num_inputs, output_format, first_channel,
+ *   num_channels, integration, ..) include/clenabled/clXEngine.h:48-52.
+ * Input: one integration in the reference host-buffer layout
+ *   [t][station][chan][pol] (lib/clXEngine_impl.cc:987-1058); IChar = int8 (re,im),
+ *   COMPLEX = c32, PACKEDXY = one byte per sample (hi nibble re, lo nibble im).
+ * Output: c32[num_channels][num_baselines][npol*npol], baseline k = s1(s1+1)/2+s2,
+ *   s1>=s2, V = sum_t x[s1] conj(x[s2]) (lib/clXEngine_impl.cc:739-810, :204-211).
+ * IChar/PACKEDXY accumulate exactly in int32 on the tensor cores; the float
+ * result is int32 * (1/127)^2 (resp. (1/7)^2) (CharToComplex :833-866).
+ * num_inputs >= 2 else CLB200_EINVAL (std::out_of_range at :106-109).            */
+CLB200_API int clb200_xengine_create(int device, int data_type, int npol, int num_inputs,
+                                     int num_channels, int integration, clb200_handle *out);
+CLB200_API long clb200_xengine_input_bytes(clb200_handle h);    /* one integration  */
+CLB200_API long clb200_xengine_output_items(clb200_handle h);   /* matrix_flat_length */
+/* xcorrelate(): H2D -> correlate -> D2H (lib/clXEngine_impl.h:150-201, .cc:1234-1299).
+ * accumulate!=0 adds into the previous result (pipeline_integration, :785-808).   */
+CLB200_API int clb200_xengine_work(clb200_handle h, const void *in, void *out_c32, int accumulate);
+/* same, but returns the exact integer accumulators int32[...][2] (IChar/PACKEDXY) */
+CLB200_API int clb200_xengine_work_i32(clb200_handle h, const void *in, int32_t *out_i32);
+CLB200_API int clb200_xengine_launch_device(clb200_handle h, const void *d_in, void *d_out_c32,
+                                            int accumulate, void *stream);
+CLB200_API int clb200_xengine_launch_device_i32(clb200_handle h, const void *d_in,
+                                                int32_t *d_out_i32, void *stream);
+/* channel-sharded variant for multi-GPU: this handle owns channels
+ * [chan_first, chan_first+chan_count) of an integration whose host layout has
+ * total_channels per station; work() gathers only that slab (cudaMemcpy2D).      */
+CLB200_API int clb200_xengine_set_shard(clb200_handle h, int total_channels, int chan_first);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLENABLED_B200_H */

@@ -93,8 +93,12 @@ ORC_API void orc_mathconst_c32(const float *in, float *out, long nitems, float k
 {
     long n = 2 * nitems;
     switch (op) {
+    case OP_EMPTY_W_COPY:   /* testCPU :278-283 copies; the OpenCL kernel string falls
+                             * through into the multiply (missing break, :187-193) --
+                             * the CPU behaviour is the one restated */
+        memcpy(out, in, sizeof(float) * n);
+        break;
     case OP_MULTIPLY:
-    case OP_EMPTY_W_COPY:   /* falls through into multiply: :187-193 */
 #pragma omp parallel for schedule(static)
         for (long i = 0; i < n; i++) out[i] = in[i] * k;
         break;

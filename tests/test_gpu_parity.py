@@ -1,0 +1,347 @@
+"""GPU parity tests: every block, through the C ABI (gr_clenabled_b200.blocks -> ctypes ->
+libclenabled_b200.so), against the oracle on the same seeded inputs, against the golden
+vectors, and -- at BASELINE.json sizes -- through size-independent properties.
+
+Tolerances: bit-exact for clMathConst / clMathOp / the X-engine integer accumulators;
+1e-5 relative (to the output's max magnitude) for FFT / filter / channelizer results,
+the figure BASELINE.json's north_star states.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gr_clenabled_b200 import blocks, capi
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+c64 = np.complex64
+GPU = (1, 1, 0, 0)        # openCLPlatformType=GPU, devSelector=first, platformId, devId
+TOL = 1e-5
+
+
+def rel_err(a, b):
+    a = np.asarray(a).astype(np.complex128)
+    b = np.asarray(b).astype(np.complex128)
+    return float(np.max(np.abs(a - b)) / max(1e-30, np.max(np.abs(b))))
+
+
+def test_device_is_blackwell():
+    assert capi.device_count() >= 1
+    buf = C.create_string_buffer(256)
+    capi.check(capi.load().clb200_device_name(0, buf, 256))
+    assert b"sm_100" in buf.value, buf.value
+
+
+# ------------------------------------------------------------------- clMathConst --
+def test_mathconst_known_answer(golden):
+    blk = blocks.clMathConst(capi.DTYPE_COMPLEX, *GPU, float(golden["mc_k"]), capi.OP_MULTIPLY)
+    assert np.array_equal(blk.work(golden["mc_in"]), golden["mc_out"])
+    assert blk.counters()["launches"] >= 1
+
+
+@pytest.mark.parametrize("op", [capi.OP_MULTIPLY, capi.OP_ADD, capi.OP_SUBTRACT, capi.OP_COMPLEX_CONJ,
+                                capi.OP_EMPTY_W_COPY])
+@pytest.mark.parametrize("n", [1, 3, 8192, 8192 * 3 + 5, 3_000_001])
+def test_mathconst_complex_bit_exact(op, n):
+    x = orc.rng_c32(n, orc.SEED_M)
+    blk = blocks.clMathConst(capi.DTYPE_COMPLEX, *GPU, 0.7071, op)
+    got = blk.work(x)
+    assert np.array_equal(got.view(np.uint32), orc.mathconst(x, 0.7071, op).view(np.uint32))
+
+
+def test_mathconst_float_int_and_setter():
+    x = orc.rng_f32(10007, orc.SEED_M)
+    blk = blocks.clMathConst(capi.DTYPE_FLOAT, *GPU, 3.0, capi.OP_ADD)
+    assert np.array_equal(blk.work(x), orc.mathconst(x, 3.0, 2))
+    blk.set_k(-1.5)
+    assert blk.k() == -1.5
+    assert np.array_equal(blk.work(x), orc.mathconst(x, -1.5, 2))
+    xi = (orc.rng_f32(5001, 3) * 1e6).astype(np.int32)
+    blk = blocks.clMathConst(capi.DTYPE_INT, *GPU, 7.9, capi.OP_MULTIPLY)
+    assert np.array_equal(blk.work(xi), orc.mathconst(xi, 7.9, 1))
+    assert blk.work(np.zeros(0, np.int32)).size == 0          # empty input
+
+
+def test_mathconst_empty_op_leaves_output_untouched():
+    blk = blocks.clMathConst(capi.DTYPE_COMPLEX, *GPU, 2.0, capi.OP_EMPTY)
+    out = np.full(100, 9 + 9j, c64)
+    blk.work(orc.rng_c32(100, 1), out=out)
+    assert np.all(out == 9 + 9j)
+
+
+# ---------------------------------------------------------------------- clMathOp --
+@pytest.mark.parametrize("op", [capi.OP_MULTIPLY, capi.OP_ADD, capi.OP_SUBTRACT, capi.OP_MULTIPLY_CONJ])
+@pytest.mark.parametrize("n", [1, 8192, 2_000_003])
+def test_mathop_complex_bit_exact(op, n):
+    a, b = orc.rng_c32(n, orc.SEED_M), orc.rng_c32(n, orc.SEED_M + 1)
+    blk = blocks.clMathOp(capi.DTYPE_COMPLEX, *GPU, op)
+    assert np.array_equal(blk.work(a, b).view(np.uint32), orc.mathop(a, b, op).view(np.uint32))
+
+
+def test_mathop_float_and_int():
+    a, b = orc.rng_f32(4099, 5), orc.rng_f32(4099, 6)
+    for op in (1, 2, 3):
+        assert np.array_equal(blocks.clMathOp(capi.DTYPE_FLOAT, *GPU, op).work(a, b), orc.mathop(a, b, op))
+    ai, bi = (a * 1e5).astype(np.int32), (b * 1e5).astype(np.int32)
+    for op in (1, 2, 3):
+        assert np.array_equal(blocks.clMathOp(capi.DTYPE_INT, *GPU, op).work(ai, bi), orc.mathop(ai, bi, op))
+
+
+def test_secondary_elementwise():
+    x = orc.rng_c32(100003, orc.SEED_M + 2)
+    f = np.abs(orc.rng_f32(100003, orc.SEED_M + 3)) + 0.01
+    g = np.abs(orc.rng_f32(100003, orc.SEED_M + 4)) + 0.01
+    assert np.allclose(blocks.clLog(*GPU, 10.0, 1.5).work(f), orc.log10(f, 10.0, 1.5), rtol=TOL, atol=TOL)
+    assert np.allclose(blocks.clSNR(*GPU, 10.0, 0.0).work(f, g), orc.snr(f, g, 10.0, 0.0), rtol=TOL, atol=TOL)
+    assert np.allclose(blocks.clComplexToMag(*GPU).work(x), orc.complex_to_mag(x), rtol=TOL)
+    assert np.allclose(blocks.clComplexToArg(*GPU).work(x), orc.complex_to_arg(x), rtol=TOL, atol=TOL)
+    m, p = blocks.clComplexToMagPhase(*GPU).work(x)
+    assert np.allclose(m, orc.complex_to_mag(x), rtol=TOL) and np.allclose(p, orc.complex_to_arg(x), rtol=TOL, atol=TOL)
+    assert np.allclose(blocks.clMagPhaseToComplex(*GPU).work(m, p), x, rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------- clFFT --
+@pytest.mark.parametrize("N", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_fft_forward_all_sizes(N):
+    nvec = 37 if N <= 1024 else 5
+    x = orc.rng_c32(N * nvec, orc.SEED_F)
+    got = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU).work(x)
+    assert rel_err(got, orc.fft(x, N, -1)) < TOL
+    want = np.fft.fft(x.astype(np.complex128).reshape(nvec, N), axis=1).reshape(-1)
+    assert rel_err(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("N", [8, 64, 2048, 8192])
+def test_fft_backward_window_shift(N, golden):
+    x = orc.rng_c32(N * 4, orc.SEED_F + 1)
+    w = orc.window_blackman(N)
+    for direction in (capi.FFT_FORWARD, capi.FFT_BACKWARD):
+        for win in (None, w):
+            for shift in (False, True):
+                blk = blocks.clFFT(N, direction, [] if win is None else win, capi.DTYPE_COMPLEX, *GPU, 0, 1, shift)
+                assert rel_err(blk.work(x), orc.fft(x, N, direction, win, shift)) < TOL, (direction, win is None, shift)
+
+
+def test_fft_tone_known_answer(golden):
+    for N in (2048, 8192):
+        got = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU).work(golden["tone_in_%d" % N])
+        assert rel_err(got, golden["tone_fft_%d" % N]) < TOL
+    # the harness configuration: tone * Blackman(8192) (test_clenabled.cc:812,835-851)
+    w = golden["win_blackman_8192"]
+    got = blocks.clFFT(8192, capi.FFT_FORWARD, w, capi.DTYPE_COMPLEX, *GPU).work(golden["tone_in_8192"])
+    assert rel_err(got, orc.fft(golden["tone_in_8192"], 8192, -1, w)) < TOL
+
+
+def test_fft_real_input_and_streams():
+    N = 1024
+    x = orc.rng_f32(N * 3, orc.SEED_F + 2)
+    got = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_FLOAT, *GPU).work(x)
+    assert rel_err(got, orc.fft_real(x, N)) < TOL
+    xs = [orc.rng_c32(N * 2, orc.SEED_F + 10 + s) for s in range(3)]
+    outs = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU, 0, 3).work_streams(xs)
+    for xi, oi in zip(xs, outs):
+        assert rel_err(oi, orc.fft(xi, N, -1)) < TOL
+
+
+def test_fft_full_size_properties():
+    """BASELINE config 2 at scale: 4096 vectors of 8192 (256 MiB in) -- Parseval, linearity and
+    forward->backward round trip, none of which needs the oracle to transform 32 Mi samples."""
+    N, nvec = 8192, 4096
+    x = orc.rng_c32(N * nvec, orc.SEED_F + 3)
+    fwd = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU)
+    inv = blocks.clFFT(N, capi.FFT_BACKWARD, [], capi.DTYPE_COMPLEX, *GPU)
+    X = fwd.work(x)
+    e_in = np.sum(np.abs(x.reshape(nvec, N).astype(np.complex128)) ** 2, axis=1)
+    e_out = np.sum(np.abs(X.reshape(nvec, N).astype(np.complex128)) ** 2, axis=1) / N
+    assert np.max(np.abs(e_out / e_in - 1)) < 1e-5
+    back = inv.work(X) / N
+    assert rel_err(back, x) < TOL
+    # spot-check 3 vectors against the oracle
+    for v in (0, nvec // 2, nvec - 1):
+        assert rel_err(X[v * N:(v + 1) * N], orc.fft(x[v * N:(v + 1) * N], N, -1)) < TOL
+
+
+# ---------------------------------------------------------------------- clFilter --
+def _stream_ref(x, taps, decim):
+    """zero-state causal convolution of the whole stream, every decim-th sample (oracle FIR)"""
+    hist = np.concatenate([np.zeros(taps.size - 1, c64), x])
+    return orc.fir(hist, taps, decim)
+
+
+@pytest.mark.parametrize("use_time", [True, False])
+@pytest.mark.parametrize("decim", [1, 4])
+def test_filter_lowpass_256_taps_streaming(golden, use_time, decim):
+    taps = np.concatenate([golden["lp_30M_1M5_283k"], [0.0]]).astype(np.float32)      # BASELINE config 3
+    x = orc.rng_c32(60000, orc.SEED_L)
+    blk = blocks.clFilter(*GPU, decim, taps, 1, 0, use_time)
+    # ragged calls: 8192-sample scheduler chunks, a multiple of nsamples, tiny and empty ones
+    cuts = [0, 8192, 8192 + 257 * 9, 8192 + 257 * 9 + 1, 8192 + 257 * 9 + 1, 30001, 60000]
+    got = np.concatenate([blk.work(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    want = _stream_ref(x, taps, decim)
+    assert got.size == want.size
+    assert rel_err(got, want) < TOL
+
+
+def test_filter_matches_reference_overlap_add(golden):
+    """same blocks the reference's fft_filter_ccf would produce (fftsize 512 / nsamples 257)"""
+    taps = golden["ramp_taps_256"]
+    x = orc.rng_c32(257 * 40, orc.SEED_L + 1)
+    ola = orc.FftFilter(taps, 1).filter(x)
+    for use_time in (False, True):
+        got = blocks.clFilter(*GPU, 1, taps, 1, 0, use_time).work(x)
+        assert rel_err(got, ola) < TOL
+    assert blocks.filter_ref_sizes(256) == (512, 257)
+
+
+@pytest.mark.parametrize("ntaps", [1, 2, 31, 300, 1000, 3000])
+def test_filter_tap_counts(ntaps):
+    taps = (orc.rng_f32(ntaps, orc.SEED_L + 2) / ntaps).astype(np.float32)
+    x = orc.rng_c32(20011, orc.SEED_L + 3)
+    want = _stream_ref(x, taps, 1)
+    for use_time in (False, True):
+        blk = blocks.clFilter(*GPU, 1, taps, 1, 0, use_time)
+        got = np.concatenate([blk.work(x[:7000]), blk.work(x[7000:])])
+        assert rel_err(got, want) < TOL, (ntaps, use_time)
+
+
+def test_filter_impulse_returns_taps_and_tap_swap(golden):
+    taps = golden["hp_1M_100k_20k"]
+    x = np.zeros(1000, c64)
+    x[0] = 1.0
+    blk = blocks.clFilter(*GPU, 1, taps)
+    y = blk.work(x)
+    assert np.allclose(y[:taps.size].real, taps, atol=1e-6) and np.allclose(y[taps.size:], 0, atol=1e-6)
+    new = golden["rrc_1M_100k_035_111"]
+    blk.set_taps2(new)                                 # history resets (clFilter_impl.cc:774-789)
+    assert np.array_equal(blk.taps(), new)
+    y = blk.work(x)
+    assert np.allclose(y[:new.size].real, new, atol=1e-6)
+
+
+def test_filter_full_size_linearity(golden):
+    """BASELINE config 3 at scale (2^22 samples): linearity + agreement of the two kernels"""
+    taps = np.concatenate([golden["lp_30M_1M5_283k"], [0.0]]).astype(np.float32)
+    n = 1 << 22
+    a, b = orc.rng_c32(n, orc.SEED_L + 4), orc.rng_c32(n, orc.SEED_L + 5)
+    f = lambda v, t=False: blocks.clFilter(*GPU, 1, taps, 1, 0, t).work(v)
+    ya, yb, yab = f(a), f(b), f((a + 2 * b).astype(c64))
+    assert rel_err(yab, ya + 2 * yb) < TOL
+    assert rel_err(f(a, True), ya) < TOL
+    assert rel_err(ya[:5000], _stream_ref(a[:5000], taps, 1)) < TOL
+
+
+# -------------------------------------------------------- clPolyphaseChannelizer --
+@pytest.mark.parametrize("M,R,T,cmap", [
+    (64, 64, 128, None), (64, 32, 128, None), (64, 64, 127, [5, 0, 63, 5]), (8, 8, 24, [3, 0, 5]),
+    (2, 2, 7, None), (16, 4, 50, None), (256, 256, 1024, None), (1024, 512, 2048, [0, 1023, 7]),
+])
+def test_pfb_vs_oracle(M, R, T, cmap):
+    taps = (orc.rng_f32(T, orc.SEED_P) * 0.1).astype(np.float32)
+    cmap = list(range(M)) if cmap is None else cmap
+    niter = 300 if M <= 64 else 21
+    x = orc.rng_c32((niter - 1) * R + T, orc.SEED_P + 1)
+    blk = blocks.clPolyphaseChannelizer(*GPU, taps, M * 4, M, R, cmap)
+    got = blk.work(x, niter)
+    assert rel_err(got, orc.pfb(x, taps, M, R, cmap, niter)) < TOL
+
+
+def test_pfb_baseline_config_tone_and_scale(golden):
+    """BASELINE config 4: 64 channels, 128-tap prototype, buf_items 65536, tone on channel 5"""
+    M = R = 64
+    taps = np.concatenate([golden["lp_pfb64"], [0.0]]).astype(np.float32)
+    niter = 65536 // R
+    n = np.arange((niter - 1) * R + taps.size)
+    x = (np.exp(2j * np.pi * 5 / M * n) + 1e-3 * orc.rng_c32(n.size, orc.SEED_P + 2)).astype(c64)
+    blk = blocks.clPolyphaseChannelizer(*GPU, taps, 65536, M, R, list(range(M)))
+    out = blk.work(x, niter)
+    assert rel_err(out, orc.pfb(x, taps, M, R, list(range(M)), niter)) < TOL
+    p = np.mean(np.abs(out.reshape(niter, M)[4:]) ** 2, axis=0)
+    assert np.argmax(p) == 5 and p[5] > 0.99
+
+
+# --------------------------------------------------------------------- clXEngine --
+def _xe(dtype, npol, A, F, T):
+    return blocks.clXEngine(*GPU, False, dtype, npol, A, 1, 0, F, T, [])
+
+
+@pytest.mark.parametrize("A,F,T,npol", [
+    (2, 1, 1, 1), (2, 3, 16, 1), (3, 17, 33, 1), (5, 4, 33, 2), (8, 16, 64, 1), (12, 256, 100, 2),
+    (16, 33, 128, 2), (17, 20, 96, 1), (32, 64, 256, 1), (32, 9, 64, 2), (24, 7, 40, 2), (64, 5, 64, 1),
+])
+def test_xengine_ichar_bit_exact(A, F, T, npol):
+    buf = orc.rng_i8(T * A * F * npol * 2, orc.SEED_X)
+    blk = _xe(capi.DTYPE_BYTE, npol, A, F, T)
+    assert blk.output_items() == F * A * (A + 1) // 2 * npol * npol       # matrix_flat_length (:204-211)
+    got = blk.work_i32(buf)
+    assert np.array_equal(got, orc.xengine_exact(buf, A, F, T, npol))
+    # float output: exact sum scaled by 1/127^2 vs the reference-order float emulation
+    vis = blk.work(buf)
+    assert rel_err(vis, orc.xengine_f32(buf, A, F, T, npol)) < TOL
+
+
+def test_xengine_extreme_values_do_not_overflow():
+    A, F, T = 32, 4, 1024
+    buf = np.full(T * A * F * 2, -128, np.int8)               # worst case |sum| = 2*128*128*1024 < 2^31
+    got = _xe(capi.DTYPE_BYTE, 1, A, F, T).work_i32(buf)
+    assert np.all(got[:, 0] == 2 * 128 * 128 * T) and np.all(got[:, 1] == 0)
+
+
+def test_xengine_identical_and_rotated_stations():
+    A, F, T = 8, 32, 512
+    one = orc.rng_i8(T * F * 2, orc.SEED_X + 1).reshape(T, 1, F, 2)
+    buf = np.repeat(one, A, axis=1).copy()
+    buf[:, 1, :, 0], buf[:, 1, :, 1] = -one[:, 0, :, 1], one[:, 0, :, 0]     # station 1 = i * station 0
+    got = _xe(capi.DTYPE_BYTE, 1, A, F, T).work_i32(buf).reshape(F, A * (A + 1) // 2, 2)
+    auto = got[:, 0, :]
+    assert np.all(auto[:, 1] == 0)
+    assert np.all(got[:, 1, 0] == 0) and np.all(got[:, 1, 1] == auto[:, 0])    # (1,0): i*|x|^2 -> pure imaginary
+    assert np.all(got[:, 5, :] == auto)                                           # (2,2) is an autocorrelation
+
+
+def test_xengine_accumulate_and_complex_and_packed():
+    A, F, T, npol = 6, 10, 64, 2
+    buf = orc.rng_i8(T * A * F * npol * 2, orc.SEED_X + 2)
+    blk = _xe(capi.DTYPE_BYTE, npol, A, F, T)
+    one = blk.work(buf)
+    two = blk.work(buf, accumulate=True)                      # pipeline_integration (:785-808)
+    assert rel_err(two, 2 * one) < 1e-6
+    xc = orc.rng_c32(T * A * F * npol, orc.SEED_X + 3)
+    got = _xe(capi.DTYPE_COMPLEX, npol, A, F, T).work(xc)
+    assert rel_err(got, orc.xengine_f32(xc, A, F, T, npol)) < TOL
+    packed = orc.rng_i8(T * A * F * npol, orc.SEED_X + 4).view(np.uint8)
+    got = _xe(capi.DTYPE_PACKEDXY, npol, A, F, T).work_i32(packed)
+    assert np.array_equal(got, orc.xengine_exact(orc.unpack4(packed), A, F, T, npol))
+
+
+def test_xengine_channel_shard_matches_full():
+    A, F, T = 8, 64, 128
+    buf = orc.rng_i8(T * A * F * 2, orc.SEED_X + 5)
+    full = _xe(capi.DTYPE_BYTE, 1, A, F, T).work_i32(buf).reshape(F, -1, 2)
+    parts = []
+    for g in range(4):
+        blk = _xe(capi.DTYPE_BYTE, 1, A, F // 4, T)
+        blk.set_shard(F, g * (F // 4))
+        parts.append(blk.work_i32(buf).reshape(F // 4, -1, 2))
+    assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+def test_xengine_baseline_config_properties():
+    """BASELINE config 5 (32 stations x 1024 channels, integration 1024, IChar): the oracle checks
+    a 16-channel slab exactly; the whole result is checked through Hermitian/real-diagonal
+    structure and additivity over time halves."""
+    A, F, T = 32, 1024, 1024
+    buf = orc.rng_i8(T * A * F * 2, orc.SEED_X + 6)
+    blk = _xe(capi.DTYPE_BYTE, 1, A, F, T)
+    got = blk.work_i32(buf).reshape(F, A * (A + 1) // 2, 2)
+    b4 = buf.reshape(T, A, F, 2)
+    slab = np.ascontiguousarray(b4[:, :, 500:516, :])
+    assert np.array_equal(got[500:516].reshape(-1, 2), orc.xengine_exact(slab, A, 16, T, 1))
+    diag = [s * (s + 1) // 2 + s for s in range(A)]
+    assert np.all(got[:, diag, 1] == 0) and np.all(got[:, diag, 0] > 0)
+    power = np.sum(b4.astype(np.int64) ** 2, axis=(0, 3))                 # [A][F]
+    assert np.array_equal(got[:, diag, 0].astype(np.int64), power.T)
+    half = _xe(capi.DTYPE_BYTE, 1, A, F, T // 2)
+    lo = half.work_i32(np.ascontiguousarray(b4[:T // 2]))
+    hi = half.work_i32(np.ascontiguousarray(b4[T // 2:]))
+    assert np.array_equal((lo + hi).reshape(got.shape), got)

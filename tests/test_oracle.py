@@ -1,0 +1,267 @@
+"""CPU tests: pin the oracle (oracle/oracle_c.c).
+
+The reference ships no golden outputs for the hot path, so the oracle
+is pinned three ways:
+  1. against the reference's OWN code where it compiles here: lib/window.cc and
+     lib/firdes.cc via oracle/_ref (live when present, and always against the
+     committed vectors tests/golden/ref_firdes_window.npz generated from it);
+  2. against the reference tools' known-answer inputs (tests/golden/kat.npz);
+  3. against independent implementations of the published maths: numpy's pocketfft,
+     scipy.signal.lfilter/upfirdn, exact int64 numpy einsum.
+"""
+import numpy as np
+import pytest
+from scipy import signal
+
+from oracle import oracle as orc
+
+c64 = np.complex64
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a.astype(np.complex128) - b.astype(np.complex128))) /
+                 max(1e-30, np.max(np.abs(b))))
+
+
+# ---- 1. reference code: window / firdes ------------------------------------------
+def test_oracle_window_matches_reference_vectors(golden):
+    assert np.array_equal(orc.window_blackman(8192), golden["win_blackman_8192"])
+    assert np.array_equal(orc.window_blackman(2048), golden["win_blackman_2048"])
+    assert np.array_equal(orc.window_hamming(255), golden["win_hamming_255"])
+    assert np.array_equal(orc.window_hamming(127), golden["win_hamming_127"])
+
+
+def test_oracle_firdes_matches_reference_vectors(golden):
+    t = orc.firdes_low_pass_hamming(1.0, 30e6, 1.5e6, 283000.0)
+    assert t.size == 255 and t.size % 2 == 1            # firdes.cc:680-683 forces odd lengths
+    assert np.array_equal(t, golden["lp_30M_1M5_283k"])
+    t = orc.firdes_low_pass_hamming(1.0, 64.0, 0.5, 1.21)
+    assert np.array_equal(t, golden["lp_pfb64"])
+    assert abs(float(np.sum(golden["lp_30M_1M5_283k"], dtype=np.float64)) - 1.0) < 1e-6   # unit DC gain
+
+
+def test_golden_vectors_match_live_reference_build(golden):
+    R = orc.ref()
+    if R is None:
+        pytest.skip("oracle/_ref not built on this box (vectors were generated where it was)")
+    w = np.zeros(8192, np.float32)
+    assert R.ref_window_build(2, 8192, 6.76, w) == 8192
+    assert np.array_equal(w, golden["win_blackman_8192"])
+    buf = np.zeros(4096, np.float32)
+    n = R.ref_firdes_low_pass(1.0, 30e6, 1.5e6, 283000.0, 0, 6.76, buf, buf.size)
+    assert np.array_equal(buf[:n], golden["lp_30M_1M5_283k"])
+
+
+# ---- 2. known answers of the reference tools -------------------------------------
+def test_kat_multiply_const(golden):
+    out = orc.mathconst(golden["mc_in"], float(golden["mc_k"]), 1)
+    assert np.array_equal(out, golden["mc_out"])          # test_clenabled.cc:1342-1356
+
+
+@pytest.mark.parametrize("N", [2048, 8192])
+def test_kat_tone_single_bin(golden, N):
+    X = orc.fft(golden["tone_in_%d" % N], N)
+    assert rel_err(X, golden["tone_fft_%d" % N]) < 1e-5    # energy only in bin N-1, value i*N
+    assert abs(X[N - 1] - 1j * N) < 1e-3 * N
+
+
+# ---- 3. independent implementations -----------------------------------------------
+def test_rng_is_reproducible_and_in_range():
+    a = orc.rng_f32(1000, 7)
+    b = orc.rng_f32(500, 7, first=500)
+    assert np.array_equal(a[500:], b)
+    assert a.min() >= -1.0 and a.max() < 1.0
+    i8 = orc.rng_i8(100000, orc.SEED_X)
+    assert i8.min() == -127 and i8.max() == 127
+
+
+@pytest.mark.parametrize("op", [1, 2, 3, 4, 254])
+def test_mathconst_vs_numpy(op):
+    x = orc.rng_c32(4099, orc.SEED_M)
+    k = np.float32(0.7071)
+    out = orc.mathconst(x, float(k), op)
+    xf = x.view(np.float32)
+    want = {1: xf * k, 2: xf + k, 3: xf - k, 4: np.conj(x).view(np.float32), 254: xf}[op]
+    assert np.array_equal(out.view(np.float32), want.astype(np.float32))
+
+
+@pytest.mark.parametrize("op", [1, 2, 3, 5])
+def test_mathop_vs_numpy(op):
+    a = orc.rng_c32(2050, orc.SEED_M)
+    b = orc.rng_c32(2050, orc.SEED_M + 1)
+    out = orc.mathop(a, b, op)
+    ar, ai, br, bi = a.real, a.imag, b.real, b.imag
+    if op == 5:
+        bi = -bi
+    if op in (1, 5):      # each product and sum rounded to float32 separately
+        re = (ar * br).astype(np.float32) - (ai * bi).astype(np.float32)
+        im = (ar * bi).astype(np.float32) + (ai * br).astype(np.float32)
+    elif op == 2:
+        re, im = ar + br, ai + b.imag
+    else:
+        re, im = ar - br, ai - b.imag
+    assert np.array_equal(out.real, re.astype(np.float32))
+    assert np.array_equal(out.imag, im.astype(np.float32))
+
+
+def test_secondary_elementwise_vs_numpy():
+    x = orc.rng_c32(3000, orc.SEED_M + 2)
+    f = np.abs(orc.rng_f32(3000, orc.SEED_M + 3)) + 0.01
+    g = np.abs(orc.rng_f32(3000, orc.SEED_M + 4)) + 0.01
+    assert np.allclose(orc.log10(f, 10.0, 1.5), 10 * np.log10(f.astype(np.float64)) + 1.5, rtol=1e-6, atol=1e-6)
+    assert np.allclose(orc.snr(f, g, 10.0, 0.0), np.abs(10 * np.log10((f / g).astype(np.float64))), rtol=1e-6, atol=1e-6)
+    assert np.allclose(orc.complex_to_mag(x), np.abs(x.astype(np.complex128)), rtol=1e-6)
+    assert np.allclose(orc.complex_to_arg(x), np.angle(x.astype(np.complex128)), rtol=1e-6, atol=1e-7)
+    m, p = orc.complex_to_mag(x), orc.complex_to_arg(x)
+    assert np.allclose(orc.magphase_to_complex(m, p), x, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("N", [2, 8, 64, 1024, 8192])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_fft_vs_pocketfft(N, direction):
+    x = orc.rng_c32(N * 3, orc.SEED_F)
+    got = orc.fft(x, N, direction)
+    X = x.astype(np.complex128).reshape(3, N)
+    want = np.fft.fft(X, axis=1) if direction < 0 else np.fft.ifft(X, axis=1) * N    # scale 1.0 both ways
+    assert rel_err(got.reshape(3, N), want) < 2e-6
+
+
+def test_fft_window_and_shift_rules():
+    N = 256
+    x = orc.rng_c32(N * 2, orc.SEED_F + 1)
+    w = orc.window_blackman(N)
+    X = x.astype(np.complex128).reshape(2, N)
+    # forward: window then transform, then swap the output halves (clFFT_impl.cc:594-607)
+    want = np.fft.fftshift(np.fft.fft(X * w, axis=1), axes=1)
+    assert rel_err(orc.fft(x, N, -1, w, True).reshape(2, N), want) < 2e-6
+    # backward + shift: input halves swapped on upload, THEN the window (:548-553, :566-580)
+    want = np.fft.ifft(np.fft.fftshift(X, axes=1) * w, axis=1) * N
+    assert rel_err(orc.fft(x, N, 1, w, True).reshape(2, N), want) < 2e-6
+
+
+def test_fft_real_input_full_hermitian_spectrum():
+    N = 512
+    x = orc.rng_f32(N * 2, orc.SEED_F + 2)
+    want = np.fft.fft(x.astype(np.float64).reshape(2, N), axis=1)
+    assert rel_err(orc.fft_real(x, N).reshape(2, N), want) < 2e-6
+
+
+@pytest.mark.parametrize("decim", [1, 4])
+def test_fir_vs_lfilter(golden, decim):
+    taps = golden["lp_30M_1M5_283k"]
+    x = orc.rng_c32(5000, orc.SEED_L)
+    hist = np.concatenate([np.zeros(taps.size - 1, c64), x])
+    got = orc.fir(hist, taps, decim)
+    want = signal.lfilter(taps.astype(np.float64), 1.0, x.astype(np.complex128))[::decim]
+    assert got.size == want.size and rel_err(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("decim", [1, 2])
+def test_fft_filter_overlap_add_vs_lfilter(golden, decim):
+    taps = np.concatenate([golden["lp_30M_1M5_283k"], [0.0]]).astype(np.float32)     # 256 taps
+    assert orc.fftfilt_sizes(256) == (512, 257)                                      # fft_filter.cc:77-78
+    assert orc.fftfilt_sizes(300) == (1024, 725)
+    f = orc.FftFilter(taps, decim)
+    x = orc.rng_c32(257 * 2 * 8, orc.SEED_L)
+    # two calls: the tail must carry across work() calls (d_tail, fft_filter.cc:172)
+    got = np.concatenate([f.filter(x[:257 * 2 * 3]), f.filter(x[257 * 2 * 3:])])
+    want = signal.lfilter(taps.astype(np.float64), 1.0, x.astype(np.complex128))
+    # dec_ctr (:160-168) carries across the nsamples blocks of a call and both calls
+    # are whole multiples of decim: the output is every decim-th sample of the stream
+    assert got.size == x.size // decim
+    assert rel_err(got, want[::decim]) < 1e-5
+
+
+def test_fft_filter_ramp_taps(golden):
+    taps = golden["ramp_taps_256"]                       # test-clfilter.cc:98-100
+    f = orc.FftFilter(taps, 1)
+    x = np.full(257 * 4, 1.0 + 0.5j, c64)                # test-clfilter.cc:77
+    got = f.filter(x)
+    want = signal.lfilter(taps.astype(np.float64), 1.0, x.astype(np.complex128))
+    assert rel_err(got, want) < 1e-5
+    assert abs(got[-1] - (1.0 + 0.5j) * taps.astype(np.float64).sum()) < 1e-3   # steady state = DC gain
+
+
+def _pfb_direct(x, taps, M, R, ch_map, niter):
+    T = taps.size
+    out = np.zeros((niter, len(ch_map)), np.complex128)
+    xd, td = x.astype(np.complex128), taps.astype(np.float64)
+    n = np.arange(M)
+    for i in range(niter):
+        filt = np.zeros(M, np.complex128)
+        for j in range(M):
+            k = np.arange(j, T, M)
+            filt[(j + i * (M - R)) % M] = np.sum(xd[i * R - k + T - 1] * td[k])
+        spec = np.array([np.sum(filt * np.exp(2j * np.pi * n * c / M)) for c in range(M)])
+        out[i] = spec[list(ch_map)]
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("M,R,T", [(8, 8, 24), (8, 4, 19), (64, 64, 128)])
+def test_pfb_vs_direct_definition(M, R, T):
+    taps = (orc.rng_f32(T, orc.SEED_P) * 0.1).astype(np.float32)
+    niter = 6
+    x = orc.rng_c32((niter - 1) * R + T, orc.SEED_P + 1)
+    ch_map = list(range(M)) if M == 64 else [3, 0, 5]
+    got = orc.pfb(x, taps, M, R, ch_map, niter)
+    assert rel_err(got, _pfb_direct(x, taps, M, R, ch_map, niter)) < 2e-6
+
+
+def test_pfb_tone_lands_in_one_channel(golden):
+    M, R = 64, 64
+    taps = np.concatenate([golden["lp_pfb64"], [0.0]]).astype(np.float32)     # 128-tap prototype
+    niter, ch = 40, 5
+    n = np.arange((niter - 1) * R + taps.size)
+    x = np.exp(2j * np.pi * ch / M * n).astype(c64)
+    out = orc.pfb(x, taps, M, R, list(range(M)), niter).reshape(niter, M)
+    p = np.mean(np.abs(out[4:]) ** 2, axis=0)
+    assert np.argmax(p) == ch
+    far = np.delete(p, [ch - 1, ch, ch + 1])              # neighbours see the transition band
+    assert p[ch] > 0.99 and far.max() < 1e-5 * p[ch]
+
+
+def _xe_numpy(buf, A, F, T, npol):
+    z = buf.reshape(T, A, F, npol, 2).astype(np.int64)
+    re, im = z[..., 0], z[..., 1]
+    out = []
+    for f in range(F):
+        for s1 in range(A):
+            for s2 in range(s1 + 1):
+                for p1 in range(npol):
+                    for p2 in range(npol):
+                        ar, ai, br, bi = re[:, s1, f, p1], im[:, s1, f, p1], re[:, s2, f, p2], im[:, s2, f, p2]
+                        out.append((np.sum(ar * br + ai * bi), np.sum(ai * br - ar * bi)))
+    return np.array(out, np.int64)
+
+
+@pytest.mark.parametrize("A,F,T,npol", [(2, 3, 16, 1), (5, 4, 33, 2), (32, 2, 64, 1)])
+def test_xengine_exact_vs_numpy(A, F, T, npol):
+    buf = orc.rng_i8(T * A * F * npol * 2, orc.SEED_X)
+    got = orc.xengine_exact(buf, A, F, T, npol)
+    assert np.array_equal(got.astype(np.int64), _xe_numpy(buf, A, F, T, npol))
+
+
+def test_xengine_identical_stations_is_autocorrelation():
+    A, F, T = 4, 2, 128
+    one = orc.rng_i8(T * F * 2, orc.SEED_X).reshape(T, 1, F, 2)
+    buf = np.repeat(one, A, axis=1).copy()
+    got = orc.xengine_exact(buf, A, F, T, 1).reshape(F, A * (A + 1) // 2, 2)
+    assert np.all(got[:, :, 1] == 0)                      # imaginary part exactly 0
+    assert np.all(got[:, :, 0] == got[:, :1, 0])          # every baseline = the autocorrelation
+
+
+def test_xengine_float_emulation_close_to_exact():
+    A, F, T = 6, 3, 256
+    buf = orc.rng_i8(T * A * F * 2, orc.SEED_X + 1)
+    exact = orc.xengine_exact(buf, A, F, T, 1).astype(np.float64) / (127.0 * 127.0)
+    f32 = orc.xengine_f32(buf, A, F, T, 1)
+    scale = np.max(np.abs(exact))
+    assert np.max(np.abs(f32.real - exact[:, 0])) / scale < 1e-5
+    assert np.max(np.abs(f32.imag - exact[:, 1])) / scale < 1e-5
+
+
+def test_unpack4_lut():
+    b = np.arange(256, dtype=np.uint8)
+    out = orc.unpack4(b).reshape(256, 2)
+    lut = np.array([0, 1, 2, 3, 4, 5, 6, 7, 0, -7, -6, -5, -4, -3, -2, -1])   # clXEngine_impl.cc:833
+    assert np.array_equal(out[:, 0], lut[b >> 4]) and np.array_equal(out[:, 1], lut[b & 15])
