@@ -20,53 +20,53 @@ using namespace clb200::fftdev;
 
 namespace {
 
-enum : int { F_INVERSE = 1, F_SHIFT = 2, F_REAL_IN = 4 };
 
-template <int LOGN, int EPT, int BATCH, int MINB>
+// MODE bit 0: inverse (re/im swapped on load and store), bit 1: real input
+template <int LOGN, int EPT, int BATCH, int MINB, int MODE>
 __global__ void __launch_bounds__((1 << LOGN) / EPT * BATCH, MINB)
 k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
-      const float2 *__restrict__ tw, const float *__restrict__ win, int flags)
+      const float2 *__restrict__ tw, const float *__restrict__ win, int shift)
 {
     using P = Plan<LOGN, EPT>;
     constexpr int N = P::N, T = P::T;
+    constexpr bool inverse = MODE & 1, real_in = MODE & 2;
     extern __shared__ __align__(16) float2 smem[];
 
     const int tb = (BATCH == 1) ? 0 : threadIdx.x / T;     // transform within the CTA
     const int lt = (BATCH == 1) ? threadIdx.x : threadIdx.x % T;
     float2 *buf = smem + tb * P::SMEM_F2;
-    const bool inverse = flags & F_INVERSE;
-    const bool real_in = flags & F_REAL_IN;
-    // forward+shift swaps the OUTPUT halves, backward+shift swaps the INPUT halves
-    const int in_xor = ((flags & F_SHIFT) && inverse) ? (N >> 1) : 0;
-    const int out_xor = ((flags & F_SHIFT) && !inverse) ? (N >> 1) : 0;
+    // forward+shift swaps the OUTPUT halves, backward+shift swaps the INPUT halves.
+    // (lt + c) ^ N/2 == lt + (c ^ N/2) for the per-thread offsets c (multiples of T),
+    // so the half swap is a choice between two base pointers per compile-time c.
+    const int in_x = (shift && inverse) ? (N >> 1) : 0;
+    const int out_x = (shift && !inverse) ? (N >> 1) : 0;
 
     const long ntile = (nvec + BATCH - 1) / BATCH;
     for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const long v = tile * BATCH + tb;
         const bool active = v < nvec;
-        const float2 *src = in + v * N;
-        const float *srcf = reinterpret_cast<const float *>(in) + v * N;
-        float2 *dst = out + v * N;
         float2 x[EPT];
 
         if (active) {
-#pragma unroll
-            for (int e = 0; e < EPT; e++) {
-                const int idx = in_index<P, EPT>(lt, e);
-                if (real_in) x[e] = make_float2(__ldcs(srcf + (idx ^ in_xor)), 0.0f);
-                else x[e] = __ldcs(src + (idx ^ in_xor));
-            }
+            const float2 *src_up = in + v * N + lt + in_x, *src_dn = in + v * N + lt - in_x;
+            const float *srf_up = reinterpret_cast<const float *>(in) + v * N + lt + in_x;
+            const float *srf_dn = reinterpret_cast<const float *>(in) + v * N + lt - in_x;
+            static_for<0, EPT>([&](auto e_) {
+                constexpr int e = decltype(e_)::value;
+                constexpr int c = in_index<P, EPT>(0, e);
+                float2 a;
+                if constexpr (real_in) a = make_float2(__ldcs(((c & (N >> 1)) ? srf_dn : srf_up) + c), 0.0f);
+                else a = __ldcs(((c & (N >> 1)) ? src_dn : src_up) + c);
+                x[e] = inverse ? make_float2(a.y, a.x) : a;
+            });
             if (win != nullptr) {
-#pragma unroll
-                for (int e = 0; e < EPT; e++) {
-                    const float w = __ldg(win + in_index<P, EPT>(lt, e));
+                const float *wp = win + lt;
+                static_for<0, EPT>([&](auto e_) {
+                    constexpr int e = decltype(e_)::value;
+                    const float w = __ldg(wp + in_index<P, EPT>(0, e));
                     x[e].x *= w;
                     x[e].y *= w;
-                }
-            }
-            if (inverse) {
-#pragma unroll
-                for (int e = 0; e < EPT; e++) x[e] = make_float2(x[e].y, x[e].x);
+                });
             }
         } else {
 #pragma unroll
@@ -76,9 +76,11 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
         fft_core<P, EPT>(x, buf, lt, tw);
 
         if (active) {
-            for_each_output<P, EPT>(x, lt, [&](int o, float2 a) {
+            float2 *dst_up = out + v * N + lt + out_x, *dst_dn = out + v * N + lt - out_x;
+            for_each_output_c<P, EPT>(x, [&](auto c_, float2 a) {
+                constexpr int c = decltype(c_)::value;
                 if (inverse) a = make_float2(a.y, a.x);
-                __stcs(dst + (o ^ out_xor), a);
+                __stcs(((c & (N >> 1)) ? dst_dn : dst_up) + c, a);
             });
         }
     }
@@ -88,7 +90,7 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
 struct FftVariant {
     int logn, ept, batch, threads, smem_bytes, tw_total, max_ctas_per_sm;
     void (*fill_tw)(std::vector<float2> &);
-    void (*kernel)(const float2 *, float2 *, long, const float2 *, const float *, int);
+    void (*kernel[3])(const float2 *, float2 *, long, const float2 *, const float *, int);
 };
 
 template <int LOGN, int EPT>
@@ -119,7 +121,9 @@ FftVariant make_variant()
     v.tw_total = P::TW_TOTAL;
     v.max_ctas_per_sm = MINB;
     v.fill_tw = &fill_tw_t<LOGN, EPT>;
-    v.kernel = &k_fft<LOGN, EPT, BATCH, MINB>;
+    v.kernel[0] = &k_fft<LOGN, EPT, BATCH, MINB, 0>;     // forward
+    v.kernel[1] = &k_fft<LOGN, EPT, BATCH, MINB, 1>;     // backward
+    v.kernel[2] = &k_fft<LOGN, EPT, BATCH, MINB, 2>;     // forward, real input
     return v;
 }
 
@@ -132,10 +136,10 @@ const FftVariant *pick_variant(int logn)
         make_variant<4, 4, 32, 4>(),    make_variant<5, 8, 32, 4>(),   make_variant<6, 8, 32, 4>(),
         make_variant<7, 8, 16, 4>(),    make_variant<8, 16, 16, 2>(),  make_variant<9, 8, 4, 4>(),
         make_variant<10, 16, 4, 2>(),   make_variant<11, 16, 2, 2>(),  make_variant<12, 16, 1, 2>(),
-        make_variant<13, 16, 1, 2>(),   make_variant<14, 16, 1, 1>(),
+        make_variant<13, 32, 1, 2>(),   make_variant<14, 16, 1, 1>(),
     };
     static const FftVariant alt[] = {
-        make_variant<13, 32, 1, 2>(),   // CLB200_FFT_VARIANT=1
+        make_variant<13, 16, 1, 2>(),   // CLB200_FFT_VARIANT=1
         make_variant<13, 32, 1, 1>(),   // 2
         make_variant<13, 16, 1, 1>(),   // 3
         make_variant<13, 8, 1, 1>(),    // 4
@@ -151,7 +155,7 @@ const FftVariant *pick_variant(int logn)
 }
 
 struct Fft : clb200_block {
-    int n = 0, logn = 0, dir = 0, dtype = 0, shift = 0;
+    int n = 0, logn = 0, dir = 0, dtype = 0, shift = 0, mode = 0;
     bool has_window = false;
     const FftVariant *var = nullptr;
     Buf d_tw, d_win;
@@ -168,13 +172,11 @@ int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st
 {
     if (nvec <= 0) return CLB200_OK;
     const FftVariant *v = f->var;
-    int flags = (f->dir > 0 ? F_INVERSE : 0) | (f->shift ? F_SHIFT : 0) |
-                (f->dtype == CLB200_DTYPE_FLOAT ? F_REAL_IN : 0);
     long ntile = (nvec + v->batch - 1) / v->batch;
     int grid = grid_for(ntile, device_sm_count(f->device), f->resident);
-    v->kernel<<<grid, v->threads, v->smem_bytes, st>>>(
+    v->kernel[f->mode]<<<grid, v->threads, v->smem_bytes, st>>>(
         (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
-        f->has_window ? (const float *)f->d_win.p : nullptr, flags);
+        f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
     CLB_CUDA(cudaGetLastError());
     f->n_launch++;
     return CLB200_OK;
@@ -213,6 +215,7 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
     f->dir = dir;
     f->dtype = dtype;
     f->shift = shift ? 1 : 0;
+    f->mode = dtype == CLB200_DTYPE_FLOAT ? 2 : (dir > 0 ? 1 : 0);
     f->var = pick_variant(f->logn);
     auto fail = [&](int rc) {
         delete f;
@@ -239,7 +242,7 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
             return fail(CLB200_ECUDA);
         }
     }
-    cudaError_t e = cudaFuncSetAttribute((const void *)f->var->kernel,
+    cudaError_t e = cudaFuncSetAttribute((const void *)f->var->kernel[f->mode],
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          f->var->smem_bytes);
     if (e != cudaSuccess) {
@@ -248,7 +251,7 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
         return fail(CLB200_ECUDA);
     }
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)f->var->kernel,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)f->var->kernel[f->mode],
                                                       f->var->threads, f->var->smem_bytes);
     if (e != cudaSuccess || occ < 1) {
         set_error("clFFT: kernel for size %d does not fit an SM (%s)", fft_size,

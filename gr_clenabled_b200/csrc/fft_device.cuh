@@ -169,6 +169,9 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
                                          const float2 *__restrict__ tw)
 {
     constexpr int N = P::N, T = P::T, NPASS = P::npass();
+    // pad(a + c) == pad(a) + pad(c) whenever c is a multiple of 16, so nearly every
+    // shared-memory address below is one per-thread base plus a compile-time offset
+    float2 *const ldp = buf + pad(lt);
     static_for<0, NPASS>([&](auto p_) {
         constexpr int p = decltype(p_)::value;
         constexpr int R = P::radix(p), NS = P::ns(p), NB = EPT / R;
@@ -177,10 +180,12 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
         constexpr int LR = ilog2(R);
 
         if constexpr (!first) {
-#pragma unroll
-            for (int u = 0; u < NB; u++)
-#pragma unroll
-                for (int r = 0; r < R; r++) x[u * R + r] = buf[pad(lt + u * T + r * STR)];
+            static_for<0, NB * R>([&](auto e_) {
+                constexpr int e = decltype(e_)::value;
+                constexpr int c = (e / R) * T + (e % R) * STR;
+                if constexpr (c % 16 == 0) x[e] = ldp[pad(c)];
+                else x[e] = buf[pad(lt + c)];
+            });
             if constexpr (!last) __syncthreads();     // all reads before the in-place writes
         }
 
@@ -197,26 +202,37 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
 
         if constexpr (!last) {
             if constexpr (first) __syncthreads();
-            static_for<0, NB>([&](auto u_) {
-                constexpr int u = decltype(u_)::value;
-                const int j = lt + u * T;
-                if constexpr (NS == 1 && (R % 2 == 0)) {
-                    // thread-contiguous run of R outputs: 128-bit stores
+            if constexpr (NS == 1 && (R % 2 == 0)) {
+                // thread-contiguous run of R outputs: 128-bit stores
+                float2 *const sp = buf + pad(lt * R);
+                static_for<0, NB>([&](auto u_) {
+                    constexpr int u = decltype(u_)::value;
                     static_for<0, R / 2>([&](auto q_) {
                         constexpr int q = decltype(q_)::value;
                         float2 a = x[u * R + bitrev(2 * q, LR)], b = x[u * R + bitrev(2 * q + 1, LR)];
-                        *reinterpret_cast<float4 *>(buf + pad(j * R + 2 * q)) =
-                            make_float4(a.x, a.y, b.x, b.y);
+                        float2 *d;
+                        if constexpr ((u * T * R) % 16 == 0) d = sp + pad(u * T * R + 2 * q);
+                        else d = buf + pad((lt + u * T) * R + 2 * q);
+                        *reinterpret_cast<float4 *>(d) = make_float4(a.x, a.y, b.x, b.y);
                     });
-                } else {
-                    const int k = j & (NS - 1);
-                    const int base = (j - k) * R + k;
+                });
+            } else {
+                const int k0 = lt & (NS - 1);
+                float2 *const sp = buf + pad((lt - k0) * R + k0);
+                static_for<0, NB>([&](auto u_) {
+                    constexpr int u = decltype(u_)::value;
                     static_for<0, R>([&](auto r_) {
                         constexpr int r = decltype(r_)::value;
-                        buf[pad(base + r * NS)] = x[u * R + bitrev(r, LR)];
+                        // j = lt + u*T keeps k when NS divides T; the tile moves by u*T*R
+                        if constexpr ((u * T) % NS == 0 && (u * T * R) % 16 == 0 && NS % 16 == 0) {
+                            sp[pad(u * T * R + r * NS)] = x[u * R + bitrev(r, LR)];
+                        } else {
+                            const int j = lt + u * T, k = j & (NS - 1);
+                            buf[pad((j - k) * R + k + r * NS)] = x[u * R + bitrev(r, LR)];
+                        }
                     });
-                }
-            });
+                });
+            }
             __syncthreads();
         }
     });
@@ -244,6 +260,23 @@ __device__ __forceinline__ void for_each_output(const float2 (&x)[EPT], int lt, 
         static_for<0, R>([&](auto r_) {
             constexpr int r = decltype(r_)::value;
             f(base + r * NS, x[u * R + bitrev(r, LR)]);
+        });
+    });
+}
+
+// same, but the index is handed over as (lt + compile-time offset): for the greedy
+// plan the last pass has NS = N/R, so output (u, r) is element lt + u*T + r*NS
+template <class P, int EPT, class F>
+__device__ __forceinline__ void for_each_output_c(const float2 (&x)[EPT], F &&f)
+{
+    constexpr int NPASS = P::npass();
+    constexpr int R = P::radix(NPASS - 1), NS = P::ns(NPASS - 1), NB = EPT / R, LR = ilog2(R);
+    static_assert(NS * R == P::N, "last pass of the greedy plan spans the transform");
+    static_for<0, NB>([&](auto u_) {
+        constexpr int u = decltype(u_)::value;
+        static_for<0, R>([&](auto r_) {
+            constexpr int r = decltype(r_)::value;
+            f(std::integral_constant<int, u * P::T + r * NS>{}, x[u * R + bitrev(r, LR)]);
         });
     });
 }
