@@ -56,7 +56,7 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
                 constexpr int c = in_index<P, EPT>(0, e);
                 float2 a;
                 if constexpr (real_in) a = make_float2(__ldcs(((c & (N >> 1)) ? srf_dn : srf_up) + c), 0.0f);
-                else a = __ldcs(((c & (N >> 1)) ? src_dn : src_up) + c);
+                else a = ldg_stream(((c & (N >> 1)) ? src_dn : src_up) + c);
                 x[e] = inverse ? make_float2(a.y, a.x) : a;
             });
             if (win != nullptr) {
@@ -86,11 +86,79 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
     }
 }
 
+// Prefetching variant for the large sizes (one transform per CTA, complex input):
+// the next vector is pulled into the (padded) working buffer by the bulk-copy engine
+// -- one 16*G-byte row per thread, completion on an mbarrier -- as soon as the
+// last pass has read its inputs, so the HBM latency of vector i+1 hides behind the
+// last butterflies and the output stores of vector i.
+template <int LOGN, int EPT, int MINB, int MODE>
+__global__ void __launch_bounds__((1 << LOGN) / EPT, MINB)
+k_fft_pf(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
+         const float2 *__restrict__ tw, const float *__restrict__ win, int shift)
+{
+    using P = Plan<LOGN, EPT>;
+    constexpr int N = P::N, T = P::T, G = P::PADG, NROWS = N / G;
+    constexpr bool inverse = MODE & 1;
+    static_assert(T % G == 0 && P::npass() > 1, "prefetch kernel is for the multi-pass sizes");
+    extern __shared__ __align__(16) float2 smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P::SMEM_F2);
+    const int lt = threadIdx.x;
+    const int in_x = (shift && inverse) ? (N >> 1) : 0;
+    const int out_x = (shift && !inverse) ? (N >> 1) : 0;
+
+    if (lt == 0) mbar_init(bar, 1);
+    __syncthreads();
+    auto issue = [&](long v) {
+        if (lt == 0) mbar_expect_tx(bar, N * (uint32_t)sizeof(float2));
+#pragma unroll
+        for (int row = lt; row < NROWS; row += T)
+            bulk_g2s(smem + P::pad(row * G), in + v * N + ((row * G) ^ in_x), G * (uint32_t)sizeof(float2), bar);
+    };
+    long v = blockIdx.x;
+    uint32_t parity = 0;
+    if (v < nvec) issue(v);
+    const float2 *const ldp = smem + P::pad(lt);
+    for (; v < nvec; v += gridDim.x) {
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        float2 x[EPT];
+        static_for<0, EPT>([&](auto e_) {
+            constexpr int e = decltype(e_)::value;
+            const float2 a = ldp[P::pad(in_index<P, EPT>(0, e))];
+            x[e] = inverse ? make_float2(a.y, a.x) : a;
+        });
+        if (win != nullptr) {
+            const float *wp = win + lt;
+            static_for<0, EPT>([&](auto e_) {
+                constexpr int e = decltype(e_)::value;
+                const float w = __ldg(wp + in_index<P, EPT>(0, e));
+                x[e].x *= w;
+                x[e].y *= w;
+            });
+        }
+        const long vn = v + gridDim.x;
+        fft_core<P, EPT>(x, smem, lt, tw, [&]() {
+            __syncthreads();                    // every thread has its last-pass inputs
+            if (vn < nvec) {
+                fence_proxy_async();
+                issue(vn);
+            }
+        });
+        float2 *dst_up = out + v * N + lt + out_x, *dst_dn = out + v * N + lt - out_x;
+        for_each_output_c<P, EPT>(x, [&](auto c_, float2 a) {
+            constexpr int c = decltype(c_)::value;
+            if (inverse) a = make_float2(a.y, a.x);
+            __stcs(((c & (N >> 1)) ? dst_dn : dst_up) + c, a);
+        });
+    }
+}
+
 // ------------------------------------------------------------------ host ----
 struct FftVariant {
     int logn, ept, batch, threads, smem_bytes, tw_total, max_ctas_per_sm;
     void (*fill_tw)(std::vector<float2> &);
     void (*kernel[3])(const float2 *, float2 *, long, const float2 *, const float *, int);
+    void (*kernel_pf[2])(const float2 *, float2 *, long, const float2 *, const float *, int);   // or null
 };
 
 template <int LOGN, int EPT>
@@ -124,6 +192,11 @@ FftVariant make_variant()
     v.kernel[0] = &k_fft<LOGN, EPT, BATCH, MINB, 0>;     // forward
     v.kernel[1] = &k_fft<LOGN, EPT, BATCH, MINB, 1>;     // backward
     v.kernel[2] = &k_fft<LOGN, EPT, BATCH, MINB, 2>;     // forward, real input
+    v.kernel_pf[0] = v.kernel_pf[1] = nullptr;
+    if constexpr (BATCH == 1 && LOGN >= 12) {
+        v.kernel_pf[0] = &k_fft_pf<LOGN, EPT, MINB, 0>;
+        v.kernel_pf[1] = &k_fft_pf<LOGN, EPT, MINB, 1>;
+    }
     return v;
 }
 
@@ -160,6 +233,7 @@ struct Fft : clb200_block {
     const FftVariant *var = nullptr;
     Buf d_tw, d_win;
     int resident = 1;     // CTAs per SM the launch is sized for
+    bool use_pf = false;  // bulk-copy prefetching kernel available and enabled
     ~Fft() override
     {
         DeviceGuard g(device);
@@ -174,9 +248,16 @@ int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st
     const FftVariant *v = f->var;
     long ntile = (nvec + v->batch - 1) / v->batch;
     int grid = grid_for(ntile, device_sm_count(f->device), f->resident);
-    v->kernel[f->mode]<<<grid, v->threads, v->smem_bytes, st>>>(
-        (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
-        f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
+    // the bulk-copy kernel needs 16 B aligned rows; anything else takes the plain one
+    const bool pf = f->use_pf && (((uintptr_t)d_in & 15) == 0);
+    if (pf)
+        v->kernel_pf[f->mode]<<<std::min<long>(grid, nvec), v->threads, v->smem_bytes + 16, st>>>(
+            (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
+            f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
+    else
+        v->kernel[f->mode]<<<grid, v->threads, v->smem_bytes, st>>>(
+            (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
+            f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
     CLB_CUDA(cudaGetLastError());
     f->n_launch++;
     return CLB200_OK;
@@ -259,6 +340,18 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
         return fail(CLB200_ECUDA);
     }
     f->resident = occ;
+    // opt-in: measured on B200 it is on par (32 elements/thread) or slower (16) than the
+    // plain kernel at 8192 points -- two resident CTAs already overlap each other's loads
+    const char *pfenv = getenv("CLB200_FFT_PREFETCH");
+    if (f->mode < 2 && f->var->kernel_pf[f->mode] && pfenv && atoi(pfenv)) {
+        const void *k = (const void *)f->var->kernel_pf[f->mode];
+        int occ2 = 0;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, f->var->smem_bytes + 16) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k, f->var->threads, f->var->smem_bytes + 16) == cudaSuccess &&
+            occ2 >= occ)
+            f->use_pf = true;
+        cudaGetLastError();
+    }
     *out = f;
     return CLB200_OK;
 }

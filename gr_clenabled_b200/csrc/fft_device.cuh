@@ -17,6 +17,7 @@
 // and on store (IDFT(x) = swap(DFT(swap(x)))), so only forward twiddles exist.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdint>
 #include <type_traits>
 #include <utility>
 
@@ -106,6 +107,53 @@ __device__ __forceinline__ void dft_dif(float2 (&x)[NREG])
     });
 }
 
+// streaming 64-bit load that does not allocate in L1 (L1 is kept for the twiddle tables)
+__device__ __forceinline__ float2 ldg_stream(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+// ---- mbarrier + bulk async copy (TMA engine, 1-D) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, bytes % 16 == 0, both addresses 16 B aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 w)
 {
     return make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
@@ -113,7 +161,10 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 w)
 
 // shared-memory padding: 16 B after every 128 B (float2 units) keeps the
 // stride-R stores of the first pass and the unit-stride loads conflict-free
-__host__ __device__ constexpr int pad(int i) { return i + ((i >> 4) << 1); }
+// (granularity G = 16 float2; 32 when the first radix is 32, whose 256 B per-thread
+// runs need an odd multiple of 16 B as thread stride)
+template <int G>
+__host__ __device__ constexpr int padg(int i) { return i + ((i / G) << 1); }
 
 // Compile-time radix plan: greedy, largest radices first.
 template <int LOGN, int EPT>
@@ -151,6 +202,8 @@ struct Plan {
         return off;
     }
     static constexpr int TW_TOTAL = tw_offset(npass());
+    static constexpr int PADG = EPT >= 32 ? 32 : 16;             // padding granularity (float2)
+    __host__ __device__ static constexpr int pad(int i) { return padg<PADG>(i); }
     static constexpr int SMEM_F2 = npass() > 1 ? pad(N) : 0;    // float2 per transform
 };
 
@@ -164,14 +217,21 @@ struct Plan {
 // number of times.  The first barrier protects buf against readers of the
 // previous use (previous transform's last pass).
 // ---------------------------------------------------------------------------
-template <class P, int EPT>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// after_last_load() runs once, right after the last pass has read its inputs out of
+// shared memory (the buffer is dead from then on for this transform) -- the
+// prefetching kernel uses it to start the bulk copy of the next vector.
+template <class P, int EPT, class Hook = NoHook>
 __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
-                                         const float2 *__restrict__ tw)
+                                         const float2 *__restrict__ tw, Hook after_last_load = Hook{})
 {
     constexpr int N = P::N, T = P::T, NPASS = P::npass();
-    // pad(a + c) == pad(a) + pad(c) whenever c is a multiple of 16, so nearly every
+    // P::pad(a + c) == P::pad(a) + P::pad(c) whenever c is a multiple of the granularity, so nearly every
     // shared-memory address below is one per-thread base plus a compile-time offset
-    float2 *const ldp = buf + pad(lt);
+    float2 *const ldp = buf + P::pad(lt);
     static_for<0, NPASS>([&](auto p_) {
         constexpr int p = decltype(p_)::value;
         constexpr int R = P::radix(p), NS = P::ns(p), NB = EPT / R;
@@ -183,10 +243,11 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
             static_for<0, NB * R>([&](auto e_) {
                 constexpr int e = decltype(e_)::value;
                 constexpr int c = (e / R) * T + (e % R) * STR;
-                if constexpr (c % 16 == 0) x[e] = ldp[pad(c)];
-                else x[e] = buf[pad(lt + c)];
+                if constexpr (c % P::PADG == 0) x[e] = ldp[P::pad(c)];
+                else x[e] = buf[P::pad(lt + c)];
             });
             if constexpr (!last) __syncthreads();     // all reads before the in-place writes
+            else after_last_load();
         }
 
         static_for<0, NB>([&](auto u_) {
@@ -204,31 +265,31 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
             if constexpr (first) __syncthreads();
             if constexpr (NS == 1 && (R % 2 == 0)) {
                 // thread-contiguous run of R outputs: 128-bit stores
-                float2 *const sp = buf + pad(lt * R);
+                float2 *const sp = buf + P::pad(lt * R);
                 static_for<0, NB>([&](auto u_) {
                     constexpr int u = decltype(u_)::value;
                     static_for<0, R / 2>([&](auto q_) {
                         constexpr int q = decltype(q_)::value;
                         float2 a = x[u * R + bitrev(2 * q, LR)], b = x[u * R + bitrev(2 * q + 1, LR)];
                         float2 *d;
-                        if constexpr ((u * T * R) % 16 == 0) d = sp + pad(u * T * R + 2 * q);
-                        else d = buf + pad((lt + u * T) * R + 2 * q);
+                        if constexpr ((u * T * R) % P::PADG == 0) d = sp + P::pad(u * T * R + 2 * q);
+                        else d = buf + P::pad((lt + u * T) * R + 2 * q);
                         *reinterpret_cast<float4 *>(d) = make_float4(a.x, a.y, b.x, b.y);
                     });
                 });
             } else {
                 const int k0 = lt & (NS - 1);
-                float2 *const sp = buf + pad((lt - k0) * R + k0);
+                float2 *const sp = buf + P::pad((lt - k0) * R + k0);
                 static_for<0, NB>([&](auto u_) {
                     constexpr int u = decltype(u_)::value;
                     static_for<0, R>([&](auto r_) {
                         constexpr int r = decltype(r_)::value;
                         // j = lt + u*T keeps k when NS divides T; the tile moves by u*T*R
-                        if constexpr ((u * T) % NS == 0 && (u * T * R) % 16 == 0 && NS % 16 == 0) {
-                            sp[pad(u * T * R + r * NS)] = x[u * R + bitrev(r, LR)];
+                        if constexpr ((u * T) % NS == 0 && (u * T * R) % P::PADG == 0 && NS % P::PADG == 0) {
+                            sp[P::pad(u * T * R + r * NS)] = x[u * R + bitrev(r, LR)];
                         } else {
                             const int j = lt + u * T, k = j & (NS - 1);
-                            buf[pad((j - k) * R + k + r * NS)] = x[u * R + bitrev(r, LR)];
+                            buf[P::pad((j - k) * R + k + r * NS)] = x[u * R + bitrev(r, LR)];
                         }
                     });
                 });

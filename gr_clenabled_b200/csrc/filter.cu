@@ -81,11 +81,11 @@ k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n
             __syncthreads();      // last pass' shared-memory reads are done
             for_each_output<P, EPT>(x, lt, [&](int o, float2 a) {
                 a = cmul(a, __ldg(H + o));
-                smem[pad(o)] = make_float2(a.y, a.x);
+                smem[P::pad(o)] = make_float2(a.y, a.x);
             });
             __syncthreads();
 #pragma unroll
-            for (int e = 0; e < EPT; e++) y[e] = smem[pad(in_index<P, EPT>(lt, e))];
+            for (int e = 0; e < EPT; e++) y[e] = smem[P::pad(in_index<P, EPT>(lt, e))];
         }
 
         fft_core<P, EPT>(y, smem, lt, tw);

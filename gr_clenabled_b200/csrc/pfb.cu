@@ -31,7 +31,7 @@ k_pfb(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
 {
     using P = Plan<LOGM, EPT>;
     constexpr int M = P::N, T = P::T;
-    constexpr int LINE = (P::SMEM_F2 > pad(M)) ? P::SMEM_F2 : pad(M);   // float2 per time step
+    constexpr int LINE = (P::SMEM_F2 > P::pad(M)) ? P::SMEM_F2 : P::pad(M);   // float2 per time step
     extern __shared__ __align__(16) float2 smem[];
 
     const int tb = (BATCH == 1) ? 0 : threadIdx.x / T;
@@ -76,11 +76,11 @@ k_pfb(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
             }
         } else {
             __syncthreads();        // the last pass' reads of buf are done
-            for_each_output<P, EPT>(x, lt, [&](int o, float2 a) { buf[pad(o)] = make_float2(a.y, a.x); });
+            for_each_output<P, EPT>(x, lt, [&](int o, float2 a) { buf[P::pad(o)] = make_float2(a.y, a.x); });
             __syncthreads();
             if (active) {
                 float2 *dst = out + i * (long)nmap;
-                for (int q = lt; q < nmap; q += T) dst[q] = buf[pad(__ldg(map + q))];
+                for (int q = lt; q < nmap; q += T) dst[q] = buf[P::pad(__ldg(map + q))];
             }
             __syncthreads();        // before the next time step overwrites buf
         }
@@ -114,7 +114,7 @@ template <int LOGM, int EPT, int BATCH, int MINB>
 PfbVariant make_pfb()
 {
     using P = Plan<LOGM, EPT>;
-    constexpr int LINE = (P::SMEM_F2 > pad(P::N)) ? P::SMEM_F2 : pad(P::N);
+    constexpr int LINE = (P::SMEM_F2 > P::pad(P::N)) ? P::SMEM_F2 : P::pad(P::N);
     return PfbVariant{LOGM, BATCH, P::T * BATCH, LINE * BATCH * (int)sizeof(float2),
                       &fill_tw_p<LOGM, EPT>, &k_pfb<LOGM, EPT, BATCH, MINB>};
 }

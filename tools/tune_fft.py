@@ -14,7 +14,7 @@ x = torch.empty(N * nvec * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1
 y = torch.empty_like(x)
 sp = torch.cuda.current_stream().cuda_stream
 res = {}
-names = {0: "EPT16 512thr minb2", 1: "EPT32 256thr minb2", 2: "EPT32 256thr minb1", 3: "EPT16 512thr minb1",
+names = {0: "EPT32 256thr minb2 (default)", 1: "EPT16 512thr minb2", 2: "EPT32 256thr minb1", 3: "EPT16 512thr minb1",
          4: "EPT8 1024thr minb1", 5: "EPT8 1024thr minb2"}
 for var in [int(a) for a in sys.argv[1:]] or sorted(names):
     os.environ["CLB200_FFT_VARIANT"] = str(var)
