@@ -80,7 +80,7 @@ __host__ __device__ constexpr int mi_max()
 }
 
 // MT: row tiles (8 inputs each) per channel; WPC: warps sharing one channel; FC = 16/WPC
-template <int MT, int WPC, int Q>
+template <int MT, int WPC, int Q, int NPOL>
 __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
 {
     constexpr int FC = XE_WARPS / WPC;
@@ -89,11 +89,12 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     constexpr int CSW = MT * 16 * XE_RSW + 2;                // channel stride (words), = 2 mod 32
     constexpr int ZW = FC * CSW;                             // words per stage buffer
     constexpr int NVP = MT * 8;
-    const int npol = p.npol;
-    const int astn = NVP / npol;                             // padded station count
-    const int runw = FC * npol / 2;                          // 32-bit words per (t, station) run
-    const int nquad = 8 * astn * runw;                       // 4-t quads per stage
-    constexpr int QPT = (32 * MT * FC + XE_THREADS - 1) / XE_THREADS;
+    constexpr int npol = NPOL;
+    constexpr int ASTN = NVP / NPOL;                         // padded station count
+    constexpr int RUNW = FC * NPOL / 2;                      // 32-bit words per (t, station) run
+    constexpr int NQUAD = 8 * ASTN * RUNW;                   // 4-t quads per stage
+    constexpr int QPT = (NQUAD + XE_THREADS - 1) / XE_THREADS;
+    static_assert(RUNW >= 1, "a stage row must hold at least one 32-bit word");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
@@ -103,6 +104,33 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     const long frameb = rowb * p.A;                          // bytes per t
     const int ngroups = (p.F + FC - 1) / FC;
     const int nstage = (p.T + XE_TT - 1) / XE_TT;
+
+    // per-thread, stage-invariant description of the 4-t quads it moves:
+    // quad e -> (word wi of the run, station s, quad-in-stage q); lanes run over
+    // (wi: RUNW values, q low 2 bits) so that both the global loads (32 B runs) and
+    // the shared stores (bank = 4*wi' + q) are conflict free
+    long qsrc[QPT];          // byte offset from the group base at t = stage start
+    int qz[QPT];             // word offset of the (first channel, re) row in a stage buffer
+    int qt[QPT];             // first time step of the quad within the stage
+    int qwi[QPT];            // word index (channel validity depends on the group)
+    bool qok[QPT];
+#pragma unroll
+    for (int i = 0; i < QPT; i++) {
+        const int e = threadIdx.x + i * XE_THREADS;
+        const int wi = e % RUNW, r1 = e / RUNW;
+        const int qlo = r1 & 3, r2 = r1 >> 2;
+        const int s = r2 % ASTN, qhi = r2 / ASTN;
+        const int q = qhi * 4 + qlo;
+        const int ch_a = (NPOL == 1) ? 2 * wi : wi;
+        const int v_a = (NPOL == 1) ? s : 2 * s;
+        qsrc[i] = (long)(4 * q) * frameb + (long)s * rowb + wi * 4;
+        qz[i] = ch_a * CSW + ((v_a >> 3) * 16 + (v_a & 7)) * XE_RSW + q;
+        qt[i] = 4 * q;
+        qwi[i] = wi;
+        qok[i] = e < NQUAD && s < p.A;
+    }
+    // second sample of a word: next channel (1 pol) or the Y polarisation of the same channel
+    constexpr int ZB = (NPOL == 1) ? CSW : XE_RSW;
 
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const int f0 = grp * FC;
@@ -117,22 +145,18 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
 
         uint32_t pre[QPT][4];
         auto load_stage = [&](int st) {
+            const int8_t *sbase = gbase + (long)st * XE_TT * frameb;
+            const int trem = p.T - st * XE_TT;           // time steps left from the stage start
 #pragma unroll
             for (int i = 0; i < QPT; i++) {
-                const int e = threadIdx.x + i * XE_THREADS;
-                const int wi = e % runw, r1 = e / runw;
-                const int qlo = r1 & 3, r2 = r1 >> 2;
-                const int s = r2 % astn, qhi = r2 / astn;
-                const int t0 = st * XE_TT + (qhi * 4 + qlo) * 4;
-                // channels covered by this word must exist
-                const int chw = (npol == 1) ? 2 * wi : wi;
-                const bool ok = e < nquad && s < p.A && (f0 + chw) < p.F;
-                const bool ok2 = (npol == 1) ? (f0 + chw + 1) < p.F : true;
-                const int8_t *src = gbase + (long)t0 * frameb + (long)s * rowb + wi * 4;
+                const int chw = (NPOL == 1) ? 2 * qwi[i] : qwi[i];
+                const bool ok = qok[i] && (f0 + chw) < p.F;
+                const bool ok2 = (NPOL == 1) ? (f0 + chw + 1) < p.F : true;
+                const int8_t *src = sbase + qsrc[i];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     uint32_t w = 0;
-                    if (ok && (t0 + k) < p.T) {
+                    if (ok && (qt[i] + k) < trem) {
                         const int8_t *q = src + (long)k * frameb;
                         if (p.aligned && ok2) {
                             w = __ldg(reinterpret_cast<const unsigned int *>(q));
@@ -148,33 +172,17 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
         auto store_stage = [&](uint32_t *z) {
 #pragma unroll
             for (int i = 0; i < QPT; i++) {
-                const int e = threadIdx.x + i * XE_THREADS;
-                if (e >= nquad) continue;
-                const int wi = e % runw, r1 = e / runw;
-                const int qlo = r1 & 3, r2 = r1 >> 2;
-                const int s = r2 % astn, qhi = r2 / astn;
-                const int q = qhi * 4 + qlo;
+                if (threadIdx.x + i * XE_THREADS >= NQUAD) continue;
                 // 4x4 byte transpose: o[b] = byte b of the four time steps
                 const uint32_t lo01 = __byte_perm(pre[i][0], pre[i][1], 0x5140);
                 const uint32_t hi01 = __byte_perm(pre[i][0], pre[i][1], 0x7362);
                 const uint32_t lo23 = __byte_perm(pre[i][2], pre[i][3], 0x5140);
                 const uint32_t hi23 = __byte_perm(pre[i][2], pre[i][3], 0x7362);
-                const uint32_t o0 = __byte_perm(lo01, lo23, 0x5410);
-                const uint32_t o1 = __byte_perm(lo01, lo23, 0x7632);
-                const uint32_t o2 = __byte_perm(hi01, hi23, 0x5410);
-                const uint32_t o3 = __byte_perm(hi01, hi23, 0x7632);
-                int ch_a, ch_b, v_a, v_b;
-                if (npol == 1) {            // word = channels 2wi, 2wi+1 of input s
-                    ch_a = 2 * wi; ch_b = 2 * wi + 1; v_a = s; v_b = s;
-                } else {                    // word = channel wi, pol X and Y of station s
-                    ch_a = wi; ch_b = wi; v_a = 2 * s; v_b = 2 * s + 1;
-                }
-                const int ra = ((v_a >> 3) * 16 + (v_a & 7)) * XE_RSW;
-                const int rb = ((v_b >> 3) * 16 + (v_b & 7)) * XE_RSW;
-                z[ch_a * CSW + ra + q] = o0;                       // (re)
-                z[ch_a * CSW + ra + 8 * XE_RSW + q] = o1;          // (im)
-                z[ch_b * CSW + rb + q] = o2;
-                z[ch_b * CSW + rb + 8 * XE_RSW + q] = o3;
+                uint32_t *d = z + qz[i];
+                d[0] = __byte_perm(lo01, lo23, 0x5410);                    // first sample, re
+                d[8 * XE_RSW] = __byte_perm(lo01, lo23, 0x7632);           //               im
+                d[ZB] = __byte_perm(hi01, hi23, 0x5410);                   // second sample, re
+                d[ZB + 8 * XE_RSW] = __byte_perm(hi01, hi23, 0x7632);      //                im
             }
         };
 
@@ -266,18 +274,18 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     }
 }
 
-template <int MT, int WPC>
+template <int MT, int WPC, int NPOL>
 __global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_i8(XeParams p)
 {
     extern __shared__ __align__(16) uint32_t xe_smem[];
     if constexpr (WPC == 1) {
-        xe_body<MT, 1, 0>(p, xe_smem);
+        xe_body<MT, 1, 0, NPOL>(p, xe_smem);
     } else {
         // every warp share runs the same barrier sequence; only the tile sets differ
         const int q = (threadIdx.x >> 5) % WPC;
         static_for<0, WPC>([&](auto q_) {
             constexpr int Q = decltype(q_)::value;
-            if (q == Q) xe_body<MT, WPC, Q>(p, xe_smem);
+            if (q == Q) xe_body<MT, WPC, Q, NPOL>(p, xe_smem);
         });
     }
 }
@@ -347,14 +355,14 @@ __global__ void k_i32_to_f32(const int2 *__restrict__ in, float2 *__restrict__ o
 typedef void (*xe_kernel_t)(XeParams);
 struct XeVariant {
     int mt, wpc, fc, smem_bytes;
-    xe_kernel_t kernel;
+    xe_kernel_t kernel[2];          // [npol - 1]
 };
 template <int MT, int WPC>
 XeVariant make_xe()
 {
     constexpr int FC = XE_WARPS / WPC;
     constexpr int CSW = MT * 16 * XE_RSW + 2;
-    return XeVariant{MT, WPC, FC, 2 * FC * CSW * 4, &k_xengine_i8<MT, WPC>};
+    return XeVariant{MT, WPC, FC, 2 * FC * CSW * 4, {&k_xengine_i8<MT, WPC, 1>, &k_xengine_i8<MT, WPC, 2>}};
 }
 const XeVariant *pick_xe(int nv)
 {
@@ -445,7 +453,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
     const XeVariant *v = x->var;
     int ngroups = (x->F + v->fc - 1) / v->fc;
-    v->kernel<<<grid_for(ngroups, sms, 1), XE_THREADS, v->smem_bytes, st>>>(p);
+    v->kernel[x->npol - 1]<<<grid_for(ngroups, sms, 1), XE_THREADS, v->smem_bytes, st>>>(p);
     CLB_CUDA(cudaGetLastError());
     x->n_launch++;
     return CLB200_OK;
@@ -572,7 +580,7 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
     x->F = num_channels;
     x->T = integration;
     x->var = pick_xe(num_inputs * npol);
-    cudaError_t e = cudaFuncSetAttribute((const void *)x->var->kernel,
+    cudaError_t e = cudaFuncSetAttribute((const void *)x->var->kernel[npol - 1],
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          x->var->smem_bytes);
     if (e != cudaSuccess) {
