@@ -51,6 +51,7 @@ struct XeParams {
     float2 *out_f32;        // same shape (may be null)
     int A, npol, F, Fstride, f_off, T;
     int accumulate;         // out += result
+    int t_slice, nslice;    // time steps per work item (multiple of 32); nslice > 1 -> int32 atomics
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
 };
@@ -103,13 +104,13 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     const long rowb = (long)p.Fstride * npol * 2;            // bytes per (t, station)
     const long frameb = rowb * p.A;                          // bytes per t
     const int ngroups = (p.F + FC - 1) / FC;
-    const int nstage = (p.T + XE_TT - 1) / XE_TT;
+    const int nitems = ngroups * p.nslice;
 
     // per-thread, stage-invariant description of the 4-t quads it moves:
     // quad e -> (word wi of the run, station s, quad-in-stage q); lanes run over
     // (wi: RUNW values, q low 2 bits) so that both the global loads (32 B runs) and
     // the shared stores (bank = 4*wi' + q) are conflict free
-    long qsrc[QPT];          // byte offset from the group base at t = stage start
+    unsigned qsrc[QPT];      // byte offset from the stage base (32 x frame bytes < 4 GiB, checked on the host)
     int qz[QPT];             // word offset of the (first channel, re) row in a stage buffer
     int qt[QPT];             // first time step of the quad within the stage
     int qwi[QPT];            // word index (channel validity depends on the group)
@@ -123,7 +124,7 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
         const int q = qhi * 4 + qlo;
         const int ch_a = (NPOL == 1) ? 2 * wi : wi;
         const int v_a = (NPOL == 1) ? s : 2 * s;
-        qsrc[i] = (long)(4 * q) * frameb + (long)s * rowb + wi * 4;
+        qsrc[i] = (unsigned)((4 * q) * frameb + s * rowb + wi * 4);
         qz[i] = ch_a * CSW + ((v_a >> 3) * 16 + (v_a & 7)) * XE_RSW + q;
         qt[i] = 4 * q;
         qwi[i] = wi;
@@ -132,9 +133,17 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     // second sample of a word: next channel (1 pol) or the Y polarisation of the same channel
     constexpr int ZB = (NPOL == 1) ? CSW : XE_RSW;
 
-    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    // work item = (time slice, channel group), groups fastest so that CTAs running
+    // together read neighbouring 32 B runs of the same DRAM pages
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int grp = item % ngroups, sl = item / ngroups;
         const int f0 = grp * FC;
-        const int8_t *gbase = p.in + ((long)(p.f_off + f0)) * npol * 2;
+        const int tbeg = sl * p.t_slice;
+        const int tlen = min(p.T - tbeg, p.t_slice);
+        const int nstage = (tlen + XE_TT - 1) / XE_TT;
+        const int8_t *gbase = p.in + ((long)(p.f_off + f0)) * npol * 2 + (long)tbeg * frameb;
+        // fast path: whole group in range, no padded stations, 32-bit aligned rows
+        const bool full = p.aligned && (f0 + FC <= p.F) && (p.A == ASTN) && (NQUAD % XE_THREADS == 0);
         int acc[NT > 0 ? NT : 1][2][4];
 #pragma unroll
         for (int i = 0; i < (NT > 0 ? NT : 1); i++)
@@ -146,7 +155,17 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
         uint32_t pre[QPT][4];
         auto load_stage = [&](int st) {
             const int8_t *sbase = gbase + (long)st * XE_TT * frameb;
-            const int trem = p.T - st * XE_TT;           // time steps left from the stage start
+            const int trem = tlen - st * XE_TT;          // time steps left from the stage start
+            if (full && trem >= XE_TT) {
+                const unsigned fb = (unsigned)frameb;
+#pragma unroll
+                for (int i = 0; i < QPT; i++) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        pre[i][k] = __ldg(reinterpret_cast<const unsigned int *>(sbase + (qsrc[i] + k * fb)));
+                }
+                return;
+            }
 #pragma unroll
             for (int i = 0; i < QPT; i++) {
                 const int chw = (NPOL == 1) ? 2 * qwi[i] : qwi[i];
@@ -224,6 +243,11 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
         }
 
         // ---- epilogue: combine re/im products, scatter the lower triangle ----
+        // thread (g, tig) of row tile mi / column tile nj holds, for h = 0,1:
+        //   v1 = 8 mi + g (row input), v2 = 8 nj + 2 tig + h (column input)
+        // 1 pol : s = v;            o = f nbl + tri(s1) + s2
+        // 2 pol : s = v>>1, p = v&1; o = 4 (f nbl + tri(s1) + s2) + 2 p1 + p2,  s2 = 4 nj + tig, p2 = h
+        // off-diagonal tiles (nj < mi) are always inside the triangle
         const int f = f0 + chl;
         if constexpr (NT > 0) {
             if (f < p.F) {
@@ -231,22 +255,28 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                     constexpr int mi = decltype(mi_)::value;
                     if constexpr (owns<WPC, Q>(mi)) {
                         constexpr int tb = tile_base<MT, WPC, Q>(mi);
+                        const int v1 = mi * 8 + g;
+                        const int s1 = (NPOL == 1) ? v1 : (v1 >> 1);
+                        const bool row_ok = s1 < p.A;
+                        long ob;        // output index of column input v2 = 2 tig, nj = 0
+                        if (NPOL == 1) ob = (long)f * nbl + s1 * (s1 + 1) / 2 + 2 * tig;
+                        else ob = 4 * ((long)f * nbl + s1 * (s1 + 1) / 2 + tig) + 2 * (v1 & 1);
                         static_for<0, mi + 1>([&](auto nj_) {
                             constexpr int nj = decltype(nj_)::value;
                             const int (&C)[4] = acc[tb + nj][0];
                             const int (&D)[4] = acc[tb + nj][1];
-                            const int v1 = mi * 8 + g;
 #pragma unroll
                             for (int h = 0; h < 2; h++) {
-                                const int v2 = nj * 8 + 2 * tig + h;
                                 const int re = C[h] + D[2 + h];
                                 const int im = C[2 + h] - D[h];
-                                const int s1 = v1 / npol, p1 = v1 % npol;
-                                const int s2 = v2 / npol, p2 = v2 % npol;
-                                if (s1 < p.A && s2 <= s1) {
-                                    const long k = (long)s1 * (s1 + 1) / 2 + s2;
-                                    const long o = (((long)f * nbl + k) * npol + p1) * npol + p2;
-                                    if (p.out_i32) {
+                                bool ok = row_ok;
+                                if (nj == mi) ok = ok && ((NPOL == 1) ? (2 * tig + h <= g) : (tig <= (g >> 1)));
+                                const long o = ob + ((NPOL == 1) ? (8 * nj + h) : (16 * nj + h));
+                                if (ok) {
+                                    if (p.nslice > 1) {
+                                        atomicAdd(p.out_i32 + 2 * o, re);
+                                        atomicAdd(p.out_i32 + 2 * o + 1, im);
+                                    } else if (p.out_i32) {
                                         int2 v = make_int2(re, im);
                                         if (p.accumulate) {
                                             int2 old = reinterpret_cast<int2 *>(p.out_i32)[o];
@@ -255,7 +285,7 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                                         }
                                         reinterpret_cast<int2 *>(p.out_i32)[o] = v;
                                     }
-                                    if (p.out_f32) {
+                                    if (p.nslice == 1 && p.out_f32) {
                                         float2 v = make_float2((float)re * p.scale, (float)im * p.scale);
                                         if (p.accumulate) {
                                             float2 old = p.out_f32[o];
@@ -437,10 +467,28 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         src = (const int8_t *)x->d_unpacked.p;
         scale = 1.0f / 49.0f;
     }
+    const XeVariant *v = x->var;
+    const int ngroups = (x->F + v->fc - 1) / v->fc;
+    // split the integration over time when there are fewer channel groups than ~3 waves of CTAs
+    int nslice = std::max(1, std::min((3 * sms + ngroups - 1) / ngroups, T / 64));
+    int t_slice = ((T + nslice - 1) / nslice + XE_TT - 1) / XE_TT * XE_TT;
+    nslice = (T + t_slice - 1) / t_slice;
+    const long nout = x->out_items();
+    if (nslice > 1) {
+        // partial sums meet in an int32 buffer through atomics
+        if (out_i32 == nullptr) {
+            CLB_TRY(x->d_acc.reserve((size_t)nout * 8));
+            CLB_CUDA(cudaMemsetAsync(x->d_acc.p, 0, (size_t)nout * 8, st));
+        } else if (!accumulate) {
+            CLB_CUDA(cudaMemsetAsync(out_i32, 0, (size_t)nout * 8, st));
+        }
+    }
     XeParams p;
     p.in = src;
-    p.out_i32 = out_i32;
+    p.out_i32 = (nslice > 1 && out_i32 == nullptr) ? (int32_t *)x->d_acc.p : out_i32;
     p.out_f32 = out_f32;
+    p.t_slice = t_slice;
+    p.nslice = nslice;
     p.A = x->A;
     p.npol = x->npol;
     p.F = x->F;
@@ -451,11 +499,15 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.scale = scale;
     long rowb = (long)Fstride * x->npol * 2;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
-    const XeVariant *v = x->var;
-    int ngroups = (x->F + v->fc - 1) / v->fc;
-    v->kernel[x->npol - 1]<<<grid_for(ngroups, sms, 1), XE_THREADS, v->smem_bytes, st>>>(p);
+    v->kernel[x->npol - 1]<<<grid_for((long)ngroups * nslice, sms, 1), XE_THREADS, v->smem_bytes, st>>>(p);
     CLB_CUDA(cudaGetLastError());
     x->n_launch++;
+    if (nslice > 1 && out_f32 != nullptr) {
+        k_i32_to_f32<<<grid_for((nout + 255) / 256, sms, 8), 256, 0, st>>>(
+            (const int2 *)p.out_i32, out_f32, nout, scale, accumulate);
+        CLB_CUDA(cudaGetLastError());
+        x->n_launch++;
+    }
     return CLB200_OK;
 }
 
@@ -564,6 +616,9 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
               CLB200_EINVAL, "clXEngine: data type %d is not complex(1), byte(4) or packed-XY(6)", data_type);
     CLB_CHECK(num_channels >= 1 && integration >= 1, CLB200_EINVAL,
               "clXEngine: num_channels and integration must be positive");
+    CLB_CHECK((long)num_inputs * num_channels * npol * 2 * 32 < (1L << 31), CLB200_EINVAL,
+              "clXEngine: one time step (%d inputs x %d channels) is too large for the stage addressing",
+              num_inputs, num_channels);
     CLB_CHECK(num_inputs * npol <= 64, CLB200_EINVAL,
               "clXEngine: %d inputs x %d polarisations exceeds the 64 rows this build tiles for",
               num_inputs, npol);
