@@ -51,7 +51,7 @@ struct XeParams {
     float2 *out_f32;        // same shape (may be null)
     int A, npol, F, Fstride, f_off, T;
     int accumulate;         // out += result
-    int t_slice, nslice;    // time steps per work item (multiple of 32); nslice > 1 -> int32 atomics
+    int split;              // CTAs share channel groups: partial sums meet through int32 atomics
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
 };
@@ -104,7 +104,6 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     const long rowb = (long)p.Fstride * npol * 2;            // bytes per (t, station)
     const long frameb = rowb * p.A;                          // bytes per t
     const int ngroups = (p.F + FC - 1) / FC;
-    const int nitems = ngroups * p.nslice;
 
     // per-thread, stage-invariant description of the 4-t quads it moves:
     // quad e -> (word wi of the run, station s, quad-in-stage q); lanes run over
@@ -133,86 +132,97 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     // second sample of a word: next channel (1 pol) or the Y polarisation of the same channel
     constexpr int ZB = (NPOL == 1) ? CSW : XE_RSW;
 
-    // work item = (time slice, channel group), groups fastest so that CTAs running
-    // together read neighbouring 32 B runs of the same DRAM pages
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int grp = item % ngroups, sl = item / ngroups;
-        const int f0 = grp * FC;
-        const int tbeg = sl * p.t_slice;
-        const int tlen = min(p.T - tbeg, p.t_slice);
-        const int nstage = (tlen + XE_TT - 1) / XE_TT;
-        const int8_t *gbase = p.in + ((long)(p.f_off + f0)) * npol * 2 + (long)tbeg * frameb;
-        // fast path: whole group in range, no padded stations, 32-bit aligned rows
-        const bool full = p.aligned && (f0 + FC <= p.F) && (p.A == ASTN) && (NQUAD % XE_THREADS == 0);
-        int acc[NT > 0 ? NT : 1][2][4];
+    // Stream-K style decomposition: the (channel group, 32-step stage) pairs form one
+    // sequence, group-major; CTA c takes an equal contiguous share of it.  A share
+    // that does not cover a group's whole integration adds its partial sums into the
+    // int32 result with atomics (p.split); otherwise every CTA owns whole groups.
+    const int nst = (p.T + XE_TT - 1) / XE_TT;
+    long s0, s1;
+    if (p.split) {
+        const long total = (long)ngroups * nst;
+        s0 = total * blockIdx.x / gridDim.x;
+        s1 = total * (blockIdx.x + 1) / gridDim.x;
+    } else {
+        s0 = ((long)ngroups * blockIdx.x / gridDim.x) * nst;
+        s1 = ((long)ngroups * (blockIdx.x + 1) / gridDim.x) * nst;
+    }
+    if (s0 >= s1) return;
+
+    int acc[NT > 0 ? NT : 1][2][4];
+    auto zero_acc = [&]() {
 #pragma unroll
         for (int i = 0; i < (NT > 0 ? NT : 1); i++)
 #pragma unroll
             for (int c = 0; c < 2; c++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) acc[i][c][j] = 0;
+    };
+    zero_acc();
 
-        uint32_t pre[QPT][4];
-        auto load_stage = [&](int st) {
-            const int8_t *sbase = gbase + (long)st * XE_TT * frameb;
-            const int trem = tlen - st * XE_TT;          // time steps left from the stage start
-            if (full && trem >= XE_TT) {
-                const unsigned fb = (unsigned)frameb;
+    uint32_t pre[QPT][4];
+    auto load_stage = [&](long sg) {
+        const int grp = (int)(sg / nst), st = (int)(sg - (long)grp * nst);
+        const int f0 = grp * FC;
+        const int8_t *sbase = p.in + ((long)(p.f_off + f0)) * npol * 2 + (long)st * XE_TT * frameb;
+        const int trem = p.T - st * XE_TT;           // time steps left from the stage start
+        // fast path: whole group in range, no padded stations, 32-bit aligned rows, full stage
+        const bool full = p.aligned && (f0 + FC <= p.F) && (p.A == ASTN) && (NQUAD % XE_THREADS == 0);
+        if (full && trem >= XE_TT) {
+            const unsigned fb = (unsigned)frameb;
 #pragma unroll
-                for (int i = 0; i < QPT; i++) {
+            for (int i = 0; i < QPT; i++)
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        pre[i][k] = __ldg(reinterpret_cast<const unsigned int *>(sbase + (qsrc[i] + k * fb)));
-                }
-                return;
-            }
+                for (int k = 0; k < 4; k++)
+                    pre[i][k] = __ldg(reinterpret_cast<const unsigned int *>(sbase + (qsrc[i] + k * fb)));
+            return;
+        }
 #pragma unroll
-            for (int i = 0; i < QPT; i++) {
-                const int chw = (NPOL == 1) ? 2 * qwi[i] : qwi[i];
-                const bool ok = qok[i] && (f0 + chw) < p.F;
-                const bool ok2 = (NPOL == 1) ? (f0 + chw + 1) < p.F : true;
-                const int8_t *src = sbase + qsrc[i];
+        for (int i = 0; i < QPT; i++) {
+            const int chw = (NPOL == 1) ? 2 * qwi[i] : qwi[i];
+            const bool ok = qok[i] && (f0 + chw) < p.F;
+            const bool ok2 = (NPOL == 1) ? (f0 + chw + 1) < p.F : true;
+            const int8_t *src = sbase + qsrc[i];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    uint32_t w = 0;
-                    if (ok && (qt[i] + k) < trem) {
-                        const int8_t *q = src + (long)k * frameb;
-                        if (p.aligned && ok2) {
-                            w = __ldg(reinterpret_cast<const unsigned int *>(q));
-                        } else {
-                            w = (uint32_t)(uint8_t)q[0] | ((uint32_t)(uint8_t)q[1] << 8);
-                            if (ok2) w |= ((uint32_t)(uint8_t)q[2] << 16) | ((uint32_t)(uint8_t)q[3] << 24);
-                        }
+            for (int k = 0; k < 4; k++) {
+                uint32_t w = 0;
+                if (ok && (qt[i] + k) < trem) {
+                    const int8_t *q = src + (long)k * frameb;
+                    if (p.aligned && ok2) {
+                        w = __ldg(reinterpret_cast<const unsigned int *>(q));
+                    } else {
+                        w = (uint32_t)(uint8_t)q[0] | ((uint32_t)(uint8_t)q[1] << 8);
+                        if (ok2) w |= ((uint32_t)(uint8_t)q[2] << 16) | ((uint32_t)(uint8_t)q[3] << 24);
                     }
-                    pre[i][k] = w;
                 }
+                pre[i][k] = w;
             }
-        };
-        auto store_stage = [&](uint32_t *z) {
+        }
+    };
+    auto store_stage = [&](uint32_t *z) {
 #pragma unroll
-            for (int i = 0; i < QPT; i++) {
-                if (threadIdx.x + i * XE_THREADS >= NQUAD) continue;
-                // 4x4 byte transpose: o[b] = byte b of the four time steps
-                const uint32_t lo01 = __byte_perm(pre[i][0], pre[i][1], 0x5140);
-                const uint32_t hi01 = __byte_perm(pre[i][0], pre[i][1], 0x7362);
-                const uint32_t lo23 = __byte_perm(pre[i][2], pre[i][3], 0x5140);
-                const uint32_t hi23 = __byte_perm(pre[i][2], pre[i][3], 0x7362);
-                uint32_t *d = z + qz[i];
-                d[0] = __byte_perm(lo01, lo23, 0x5410);                    // first sample, re
-                d[8 * XE_RSW] = __byte_perm(lo01, lo23, 0x7632);           //               im
-                d[ZB] = __byte_perm(hi01, hi23, 0x5410);                   // second sample, re
-                d[ZB + 8 * XE_RSW] = __byte_perm(hi01, hi23, 0x7632);      //                im
-            }
-        };
+        for (int i = 0; i < QPT; i++) {
+            if (threadIdx.x + i * XE_THREADS >= NQUAD) continue;
+            // 4x4 byte transpose: o[b] = byte b of the four time steps
+            const uint32_t lo01 = __byte_perm(pre[i][0], pre[i][1], 0x5140);
+            const uint32_t hi01 = __byte_perm(pre[i][0], pre[i][1], 0x7362);
+            const uint32_t lo23 = __byte_perm(pre[i][2], pre[i][3], 0x5140);
+            const uint32_t hi23 = __byte_perm(pre[i][2], pre[i][3], 0x7362);
+            uint32_t *d = z + qz[i];
+            d[0] = __byte_perm(lo01, lo23, 0x5410);                    // first sample, re
+            d[8 * XE_RSW] = __byte_perm(lo01, lo23, 0x7632);           //               im
+            d[ZB] = __byte_perm(hi01, hi23, 0x5410);                   // second sample, re
+            d[ZB + 8 * XE_RSW] = __byte_perm(hi01, hi23, 0x7632);      //                im
+        }
+    };
 
-        __syncthreads();        // previous group's readers are done with zbuf
-        load_stage(0);
-        store_stage(zbuf);
-        if (nstage > 1) load_stage(1);
-        __syncthreads();
+    load_stage(s0);
+    store_stage(zbuf);
+    if (s0 + 1 < s1) load_stage(s0 + 1);
+    __syncthreads();
 
-        for (int st = 0; st < nstage; st++) {
-            const uint32_t *z = zbuf + (st & 1) * ZW + chl * CSW;
+    for (long sg = s0; sg < s1; sg++) {
+        {
+            const uint32_t *z = zbuf + (int)((sg - s0) & 1) * ZW + chl * CSW;
             if constexpr (NT > 0) {
                 int a[MMAX + 1][4];
 #pragma unroll
@@ -235,12 +245,19 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                     }
                 });
             }
-            if (st + 1 < nstage) {
-                store_stage(zbuf + ((st + 1) & 1) * ZW);
-                if (st + 2 < nstage) load_stage(st + 2);
+            // feed: next stage into the other Z buffer, the one after it into registers
+            if (sg + 1 < s1) {
+                store_stage(zbuf + (int)((sg + 1 - s0) & 1) * ZW);
+                if (sg + 2 < s1) load_stage(sg + 2);
             }
-            __syncthreads();
         }
+        const int grp = (int)(sg / nst);
+        const bool group_done = (sg + 1 == s1) || ((sg + 1) % nst == 0);
+        if (!group_done) {
+            __syncthreads();
+            continue;
+        }
+        const int f0 = grp * FC;
 
         // ---- epilogue: combine re/im products, scatter the lower triangle ----
         // thread (g, tig) of row tile mi / column tile nj holds, for h = 0,1:
@@ -273,7 +290,7 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                                 if (nj == mi) ok = ok && ((NPOL == 1) ? (2 * tig + h <= g) : (tig <= (g >> 1)));
                                 const long o = ob + ((NPOL == 1) ? (8 * nj + h) : (16 * nj + h));
                                 if (ok) {
-                                    if (p.nslice > 1) {
+                                    if (p.split) {
                                         atomicAdd(p.out_i32 + 2 * o, re);
                                         atomicAdd(p.out_i32 + 2 * o + 1, im);
                                     } else if (p.out_i32) {
@@ -285,7 +302,7 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                                         }
                                         reinterpret_cast<int2 *>(p.out_i32)[o] = v;
                                     }
-                                    if (p.nslice == 1 && p.out_f32) {
+                                    if (!p.split && p.out_f32) {
                                         float2 v = make_float2((float)re * p.scale, (float)im * p.scale);
                                         if (p.accumulate) {
                                             float2 old = p.out_f32[o];
@@ -301,6 +318,8 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                 });
             }
         }
+        zero_acc();
+        __syncthreads();
     }
 }
 
@@ -469,10 +488,11 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     }
     const XeVariant *v = x->var;
     const int ngroups = (x->F + v->fc - 1) / v->fc;
-    // split the integration over time when there are fewer channel groups than ~3 waves of CTAs
-    int nslice = std::max(1, std::min((3 * sms + ngroups - 1) / ngroups, T / 64));
-    int t_slice = ((T + nslice - 1) / nslice + XE_TT - 1) / XE_TT * XE_TT;
-    nslice = (T + t_slice - 1) / t_slice;
+    // fewer channel groups than ~2 waves of CTAs: split the integrations over time as well
+    const int nst = (T + XE_TT - 1) / XE_TT;
+    const bool split = ngroups < 2 * sms && nst > 1;
+    const int nslice = split ? 2 : 1;
+    const int grid = (int)std::min<long>(sms, split ? (long)ngroups * nst : ngroups);
     const long nout = x->out_items();
     if (nslice > 1) {
         // partial sums meet in an int32 buffer through atomics
@@ -487,8 +507,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.in = src;
     p.out_i32 = (nslice > 1 && out_i32 == nullptr) ? (int32_t *)x->d_acc.p : out_i32;
     p.out_f32 = out_f32;
-    p.t_slice = t_slice;
-    p.nslice = nslice;
+    p.split = split ? 1 : 0;
     p.A = x->A;
     p.npol = x->npol;
     p.F = x->F;
@@ -499,7 +518,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.scale = scale;
     long rowb = (long)Fstride * x->npol * 2;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
-    v->kernel[x->npol - 1]<<<grid_for((long)ngroups * nslice, sms, 1), XE_THREADS, v->smem_bytes, st>>>(p);
+    v->kernel[x->npol - 1]<<<grid, XE_THREADS, v->smem_bytes, st>>>(p);
     CLB_CUDA(cudaGetLastError());
     x->n_launch++;
     if (nslice > 1 && out_f32 != nullptr) {
