@@ -137,14 +137,14 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     // that does not cover a group's whole integration adds its partial sums into the
     // int32 result with atomics (p.split); otherwise every CTA owns whole groups.
     const int nst = (p.T + XE_TT - 1) / XE_TT;
-    long s0, s1;
+    int s0, s1;                                   // ngroups * nst < 2^31 (checked on the host)
     if (p.split) {
         const long total = (long)ngroups * nst;
-        s0 = total * blockIdx.x / gridDim.x;
-        s1 = total * (blockIdx.x + 1) / gridDim.x;
+        s0 = (int)(total * blockIdx.x / gridDim.x);
+        s1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
     } else {
-        s0 = ((long)ngroups * blockIdx.x / gridDim.x) * nst;
-        s1 = ((long)ngroups * (blockIdx.x + 1) / gridDim.x) * nst;
+        s0 = (int)((long)ngroups * blockIdx.x / gridDim.x) * nst;
+        s1 = (int)((long)ngroups * (blockIdx.x + 1) / gridDim.x) * nst;
     }
     if (s0 >= s1) return;
 
@@ -160,8 +160,8 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     zero_acc();
 
     uint32_t pre[QPT][4];
-    auto load_stage = [&](long sg) {
-        const int grp = (int)(sg / nst), st = (int)(sg - (long)grp * nst);
+    auto load_stage = [&](int sg) {
+        const int grp = sg / nst, st = sg - grp * nst;
         const int f0 = grp * FC;
         const int8_t *sbase = p.in + ((long)(p.f_off + f0)) * npol * 2 + (long)st * XE_TT * frameb;
         const int trem = p.T - st * XE_TT;           // time steps left from the stage start
@@ -220,9 +220,9 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     if (s0 + 1 < s1) load_stage(s0 + 1);
     __syncthreads();
 
-    for (long sg = s0; sg < s1; sg++) {
+    for (int sg = s0; sg < s1; sg++) {
         {
-            const uint32_t *z = zbuf + (int)((sg - s0) & 1) * ZW + chl * CSW;
+            const uint32_t *z = zbuf + ((sg - s0) & 1) * ZW + chl * CSW;
             if constexpr (NT > 0) {
                 int a[MMAX + 1][4];
 #pragma unroll
@@ -247,11 +247,11 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
             }
             // feed: next stage into the other Z buffer, the one after it into registers
             if (sg + 1 < s1) {
-                store_stage(zbuf + (int)((sg + 1 - s0) & 1) * ZW);
+                store_stage(zbuf + ((sg + 1 - s0) & 1) * ZW);
                 if (sg + 2 < s1) load_stage(sg + 2);
             }
         }
-        const int grp = (int)(sg / nst);
+        const int grp = sg / nst;
         const bool group_done = (sg + 1 == s1) || ((sg + 1) % nst == 0);
         if (!group_done) {
             __syncthreads();
@@ -638,6 +638,8 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
     CLB_CHECK((long)num_inputs * num_channels * npol * 2 * 32 < (1L << 31), CLB200_EINVAL,
               "clXEngine: one time step (%d inputs x %d channels) is too large for the stage addressing",
               num_inputs, num_channels);
+    CLB_CHECK(((long)num_channels + 3) / 4 * (((long)integration + 31) / 32) < (1L << 31), CLB200_EINVAL,
+              "clXEngine: %d channels x %d time steps exceed the stage index range", num_channels, integration);
     CLB_CHECK(num_inputs * npol <= 64, CLB200_EINVAL,
               "clXEngine: %d inputs x %d polarisations exceeds the 64 rows this build tiles for",
               num_inputs, npol);

@@ -1,0 +1,431 @@
+// blocks_impl.cc -- the gr::clenabled block classes over the C ABI (clenabled_b200.h).
+//
+// Mirrors the reference's *_impl classes (lib/clMathConst_impl.cc, clMathOp_impl.cc,
+// clFFT_impl.cc, clFilter_impl.cc, clPolyphaseChannelizer_impl.cc, clXEngine_impl.cc and
+// the secondary element-wise blocks): same io signatures, scheduler hints (set_history,
+// set_output_multiple), item semantics and error behaviour; all arithmetic happens in
+// libclenabled_b200.so.  No OpenCL, no CPU path.
+#include <clenabled/blocks.h>
+
+#include <clenabled_b200.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+namespace gr {
+namespace clenabled {
+
+namespace {
+
+int pick_device(int platformType, int devSelector, int platformId, int devId)
+{
+    int d = clb200_select_device(platformType, devSelector, platformId, devId);
+    if (d < 0) throw std::runtime_error(std::string("clenabled_b200: ") + clb200_last_error());
+    return d;
+}
+
+// ctor-time failures throw (reference ctors throw std::runtime_error / invalid_argument /
+// out_of_range); EINVAL maps to invalid_argument
+void must(int rc, bool out_of_range = false)
+{
+    if (rc == CLB200_OK) return;
+    std::string msg = clb200_last_error();
+    if (rc == CLB200_EINVAL) {
+        if (out_of_range) throw std::out_of_range(msg);
+        throw std::invalid_argument(msg);
+    }
+    throw std::runtime_error(msg);
+}
+
+// work-time failures: log and stop the block (reference: print + exit(0), GRCLBase.cpp:239-257)
+int work_failed(const char *who)
+{
+    fprintf(stderr, "%s: %s\n", who, clb200_last_error());
+    return gr::block::WORK_DONE;
+}
+
+struct Handle {
+    clb200_handle h = nullptr;
+    ~Handle() { clb200_destroy(h); }
+};
+
+size_t item_size(int idataType)
+{
+    return idataType == DTYPE_COMPLEX ? sizeof(gr_complex) : (idataType == DTYPE_FLOAT ? sizeof(float) : sizeof(int));
+}
+
+// ------------------------------------------------------------------ clMathConst --
+class clMathConst_impl : public clMathConst
+{
+    Handle d;
+
+public:
+    clMathConst_impl(int idataType, int dev, float fValue, int operatorType)
+        : gr::sync_block("clMathConst", gr::io_signature::make(1, 1, item_size(idataType)),
+                         gr::io_signature::make(1, 1, item_size(idataType)))
+    {
+        must(clb200_mathconst_create(idataType, dev, fValue, operatorType, &d.h));
+        set_output_multiple(256);       // reference: preferred work-group multiple (clMathConst_impl.cc:86-94)
+    }
+    float k() const override { return clb200_mathconst_k(d.h); }
+    void set_k(float v) override { clb200_mathconst_set_k(d.h, v); }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_mathconst_work(d.h, in[0], out[0], noutput_items) != CLB200_OK)
+            return work_failed("clMathConst");
+        return noutput_items;
+    }
+};
+
+// --------------------------------------------------------------------- clMathOp --
+class clMathOp_impl : public clMathOp
+{
+    Handle d;
+
+public:
+    clMathOp_impl(int idataType, int dev, int operatorType)
+        : gr::sync_block("clMathOp", gr::io_signature::make(2, 2, item_size(idataType)),
+                         gr::io_signature::make(1, 1, item_size(idataType)))
+    {
+        must(clb200_mathop_create(idataType, dev, operatorType, &d.h));
+        set_output_multiple(256);
+    }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (noutput_items == 0) return 0;       // clMathOp_impl.cc:367-369
+        if (clb200_mathop_work(d.h, in[0], in[1], out[0], noutput_items) != CLB200_OK)
+            return work_failed("clMathOp");
+        return noutput_items;
+    }
+};
+
+// ------------------------------------------------------------ secondary blocks --
+template <class Base>
+class unary_impl : public Base
+{
+    Handle d;
+
+public:
+    unary_impl(const char *name, int kind, size_t in_size, int dev, float n, float k)
+        : gr::sync_block(name, gr::io_signature::make(1, 1, in_size), gr::io_signature::make(1, 1, sizeof(float)))
+    {
+        must(clb200_unary_create(kind, dev, n, k, &d.h));
+    }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_unary_work(d.h, in[0], out[0], noutput_items) != CLB200_OK) return work_failed("clenabled");
+        return noutput_items;
+    }
+};
+
+class clSNR_impl : public clSNR
+{
+    Handle d;
+
+public:
+    clSNR_impl(int dev, float n, float k)
+        : gr::sync_block("clSNR", gr::io_signature::make(2, 2, sizeof(float)), gr::io_signature::make(1, 1, sizeof(float)))
+    {
+        must(clb200_snr_create(dev, n, k, &d.h));
+    }
+    int work(int n, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_snr_work(d.h, (const float *)in[0], (const float *)in[1], (float *)out[0], n) != CLB200_OK)
+            return work_failed("clSNR");
+        return n;
+    }
+};
+
+class clComplexToMagPhase_impl : public clComplexToMagPhase
+{
+    Handle d;
+
+public:
+    explicit clComplexToMagPhase_impl(int dev)
+        : gr::sync_block("clComplexToMagPhase", gr::io_signature::make(1, 1, sizeof(gr_complex)),
+                         gr::io_signature::make(2, 2, sizeof(float)))
+    {
+        must(clb200_c2magphase_create(dev, &d.h));
+    }
+    int work(int n, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_c2magphase_work(d.h, in[0], (float *)out[0], (float *)out[1], n) != CLB200_OK)
+            return work_failed("clComplexToMagPhase");
+        return n;
+    }
+};
+
+class clMagPhaseToComplex_impl : public clMagPhaseToComplex
+{
+    Handle d;
+
+public:
+    explicit clMagPhaseToComplex_impl(int dev)
+        : gr::sync_block("clMagPhaseToComplex", gr::io_signature::make(2, 2, sizeof(float)),
+                         gr::io_signature::make(1, 1, sizeof(gr_complex)))
+    {
+        must(clb200_magphase2c_create(dev, &d.h));
+    }
+    int work(int n, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_magphase2c_work(d.h, (const float *)in[0], (const float *)in[1], out[0], n) != CLB200_OK)
+            return work_failed("clMagPhaseToComplex");
+        return n;
+    }
+};
+
+// ------------------------------------------------------------------------ clFFT --
+class clFFT_impl : public clFFT
+{
+    Handle d;
+    int d_fft_size, d_num_streams;
+
+public:
+    clFFT_impl(int fftSize, int dir, const std::vector<float> &window, int idataType, int dev, int num_streams,
+               bool shift)
+        : gr::sync_block("clFFT",
+                         gr::io_signature::make(num_streams, num_streams, fftSize * item_size(idataType)),
+                         gr::io_signature::make(num_streams, num_streams, fftSize * sizeof(gr_complex))),
+          d_fft_size(fftSize), d_num_streams(num_streams)
+    {
+        // lib/clFFT_impl.cc:74-76
+        if (!window.empty() && (int)window.size() != fftSize)
+            throw std::runtime_error("fft_vcc: window not the same length as fft_size");
+        if (num_streams < 1) throw std::invalid_argument("clFFT: num_streams must be >= 1");
+        must(clb200_fft_create(fftSize, dir, window.empty() ? nullptr : window.data(), (int)window.size(),
+                               idataType, dev, shift ? 1 : 0, &d.h));
+    }
+    // noutput_items counts vectors (lib/clFFT_impl.cc:637-654)
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_fft_work_streams(d.h, in.data(), out.data(), d_num_streams, noutput_items) != CLB200_OK)
+            return work_failed("clFFT");
+        return noutput_items;
+    }
+};
+
+// --------------------------------------------------------------------- clFilter --
+class clFilter_impl : public clFilter
+{
+    Handle d;
+    int d_nthreads;
+
+public:
+    clFilter_impl(int dev, int decimation, const std::vector<float> &taps, int nthreads, bool use_time)
+        : gr::sync_decimator("clFilter", gr::io_signature::make(1, 1, sizeof(gr_complex)),
+                             gr::io_signature::make(1, 1, sizeof(gr_complex)), decimation),
+          d_nthreads(nthreads)
+    {
+        must(clb200_filter_create(dev, decimation, taps.data(), (int)taps.size(), use_time ? 1 : 0, &d.h));
+        // The reference sets set_history(ntaps) (clFilter_impl.cc:78) because its kernels read
+        // the overlap out of the scheduler's buffer.  Here the last ntaps-1 samples live in the
+        // handle on the device, so the block consumes exactly noutput*decimation NEW samples
+        // and in[0] is the first new one: history stays 1.
+    }
+    void set_taps2(const std::vector<float> &taps) override
+    {
+        if (clb200_filter_set_taps(d.h, taps.data(), (int)taps.size()) != CLB200_OK)
+            throw std::invalid_argument(clb200_last_error());
+    }
+    std::vector<float> taps() const override
+    {
+        std::vector<float> t(clb200_filter_ntaps(d.h));
+        clb200_filter_get_taps(d.h, t.data(), (int)t.size());
+        return t;
+    }
+    void set_nthreads(int n) override { d_nthreads = n; }      // accepted, unused like the reference (:57)
+    int nthreads() const override { return d_nthreads; }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        long n_out = 0;
+        if (clb200_filter_work(d.h, in[0], (long)noutput_items * decimation(), out[0], &n_out) != CLB200_OK)
+            return work_failed("clFilter");
+        return (int)n_out;
+    }
+};
+
+// ------------------------------------------------------- clPolyphaseChannelizer --
+class clPolyphaseChannelizer_impl : public clPolyphaseChannelizer
+{
+    Handle d;
+    int d_ntaps, d_buf_items, d_M, d_R, d_nmap;
+
+public:
+    clPolyphaseChannelizer_impl(int dev, const std::vector<float> &taps, int buf_items, int num_channels,
+                                int ninputs_per_iter, const std::vector<int> &ch_map)
+        : gr::block("clPolyphaseChannelizer", gr::io_signature::make(1, 1, sizeof(gr_complex)),
+                    gr::io_signature::make(1, 1, sizeof(gr_complex))),
+          d_ntaps((int)taps.size()), d_buf_items(buf_items), d_M(num_channels), d_R(ninputs_per_iter),
+          d_nmap((int)ch_map.size())
+    {
+        must(clb200_pfb_create(dev, taps.data(), d_ntaps, buf_items, num_channels, ninputs_per_iter, ch_map.data(),
+                               d_nmap, &d.h));
+        set_history(d_ntaps);                                        // :63
+        set_output_multiple(d_nmap * d_buf_items / d_R);             // :64
+    }
+    void forecast(int noutput_items, gr_vector_int &req) override
+    {
+        // one call = buf_items/R time steps, which read (steps-1)*R + ntaps samples; the
+        // reference asks for R*nout/nmap + history - M (:77-81), which is short when R < M
+        req[0] = d_R * noutput_items / d_nmap + (int)history() - d_R;
+    }
+    int general_work(int, gr_vector_int &, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        const long niter = d_buf_items / d_R;
+        if (clb200_pfb_work(d.h, in[0], out[0], niter) != CLB200_OK) return work_failed("clPolyphaseChannelizer");
+        consume_each(d_buf_items);                                   // :105
+        return (int)(d_nmap * niter);                                // :108
+    }
+};
+
+// -------------------------------------------------------------------- clXEngine --
+class clXEngine_impl : public clXEngine
+{
+    Handle d;
+    int d_data_type, d_npol, d_num_inputs, d_num_channels, d_integration, d_pipeline;
+    bool d_disable_output;
+    size_t d_sample_bytes;
+    std::vector<char> d_buf;                  // one integration, [t][station][chan][pol]
+    std::vector<gr_complex> d_matrix;
+    int d_tracker = 0, d_pipeline_count = 0;
+
+public:
+    clXEngine_impl(int dev, int data_type, int polarization, int num_inputs, int num_channels, int integration,
+                   bool disable_output, int pipeline_integration)
+        : gr::block("clXEngine",
+                    gr::io_signature::make(2, num_inputs * (data_type == DTYPE_PACKEDXY ? 1 : polarization),
+                                           num_channels * (data_type == DTYPE_PACKEDXY ? 2
+                                                           : data_type == DTYPE_BYTE   ? 2
+                                                                                       : (int)sizeof(gr_complex))),
+                    gr::io_signature::make(0, 0, 0)),
+          d_data_type(data_type), d_npol(polarization), d_num_inputs(num_inputs), d_num_channels(num_channels),
+          d_integration(integration), d_pipeline(pipeline_integration), d_disable_output(disable_output)
+    {
+        must(clb200_xengine_create(dev, data_type, polarization, num_inputs, num_channels, integration, &d.h),
+             num_inputs < 2);                   // std::out_of_range, clXEngine_impl.cc:106-109
+        d_sample_bytes = data_type == DTYPE_COMPLEX ? sizeof(gr_complex) : (data_type == DTYPE_BYTE ? 2 : 1);
+        d_buf.resize((size_t)clb200_xengine_input_bytes(d.h));
+        d_matrix.resize((size_t)clb200_xengine_output_items(d.h));
+        message_port_register_out(pmt::mp("xcorr"));                 // :294-295
+        message_port_register_out(pmt::mp("sync"));
+    }
+    void forecast(int noutput_items, gr_vector_int &req) override
+    {
+        for (auto &r : req) r = noutput_items;                       // :385-390
+    }
+    // work_processor (:918-1142): marshal the port vectors of each time step into the
+    // integration buffer; a full buffer is correlated and published as ("triang_matrix" . c32vector)
+    int general_work(int noutput_items, gr_vector_int &, gr_vector_const_void_star &in, gr_vector_void_star &) override
+    {
+        gr::thread::scoped_lock guard(d_setlock);
+        int n = std::min(noutput_items, d_integration - d_tracker);
+        const size_t vec = (size_t)d_num_channels * d_sample_bytes;          // bytes of one port item
+        const size_t row = vec * d_npol;                                      // one station, one time step
+        const size_t frame = row * d_num_inputs;
+        for (int t = 0; t < n; t++) {
+            char *dst = d_buf.data() + (size_t)(d_tracker + t) * frame;
+            for (int s = 0; s < d_num_inputs; s++) {
+                if (d_npol == 1 || d_data_type == DTYPE_PACKEDXY) {
+                    memcpy(dst + s * row, (const char *)in[s] + (size_t)t * row, row);
+                } else {                                                      // interleave X,Y per channel (:1010-1057)
+                    const char *x = (const char *)in[s] + (size_t)t * vec;
+                    const char *y = (const char *)in[s + d_num_inputs] + (size_t)t * vec;
+                    char *o = dst + s * row;
+                    for (int c = 0; c < d_num_channels; c++) {
+                        memcpy(o + (2 * c) * d_sample_bytes, x + c * d_sample_bytes, d_sample_bytes);
+                        memcpy(o + (2 * c + 1) * d_sample_bytes, y + c * d_sample_bytes, d_sample_bytes);
+                    }
+                }
+            }
+        }
+        d_tracker += n;
+        if (d_tracker == d_integration) {
+            const bool accumulate = d_pipeline > 1 && d_pipeline_count > 0;   // :785-808
+            if (clb200_xengine_work(d.h, d_buf.data(), d_matrix.data(), accumulate ? 1 : 0) != CLB200_OK)
+                return work_failed("clXEngine");
+            d_tracker = 0;
+            d_pipeline_count++;
+            if (d_pipeline < 2 || d_pipeline_count >= d_pipeline) {
+                d_pipeline_count = 0;
+                if (!d_disable_output)
+                    message_port_pub(pmt::mp("xcorr"),
+                                     pmt::cons(pmt::string_to_symbol("triang_matrix"),
+                                               pmt::init_c32vector(d_matrix.size(), d_matrix.data())));   // :1076-1080
+            }
+        }
+        for (size_t p = 0; p < in.size(); p++) consume((int)p, n);            // :1228-1231
+        return n;
+    }
+};
+
+} // namespace
+
+// ---------------------------------------------------------------- factories --
+clMathConst::sptr clMathConst::make(int idataType, int plat, int sel, int pid, int did, float fValue,
+                                    int operatorType, int)
+{
+    return gnuradio::get_initial_sptr(new clMathConst_impl(idataType, pick_device(plat, sel, pid, did), fValue, operatorType));
+}
+clMathOp::sptr clMathOp::make(int idataType, int plat, int sel, int pid, int did, int operatorType, int)
+{
+    return gnuradio::get_initial_sptr(new clMathOp_impl(idataType, pick_device(plat, sel, pid, did), operatorType));
+}
+clLog::sptr clLog::make(int plat, int sel, int pid, int did, float n, float k, int)
+{
+    return gnuradio::get_initial_sptr(new unary_impl<clLog>("clLog", CLB200_UNARY_LOG10, sizeof(float),
+                                                            pick_device(plat, sel, pid, did), n, k));
+}
+clSNR::sptr clSNR::make(int plat, int sel, int pid, int did, float n, float k, int)
+{
+    return gnuradio::get_initial_sptr(new clSNR_impl(pick_device(plat, sel, pid, did), n, k));
+}
+clComplexToMag::sptr clComplexToMag::make(int plat, int sel, int pid, int did, int)
+{
+    return gnuradio::get_initial_sptr(new unary_impl<clComplexToMag>("clComplexToMag", CLB200_UNARY_COMPLEX_TO_MAG,
+                                                                     sizeof(gr_complex), pick_device(plat, sel, pid, did), 0, 0));
+}
+clComplexToArg::sptr clComplexToArg::make(int plat, int sel, int pid, int did, int)
+{
+    return gnuradio::get_initial_sptr(new unary_impl<clComplexToArg>("clComplexToArg", CLB200_UNARY_COMPLEX_TO_ARG,
+                                                                     sizeof(gr_complex), pick_device(plat, sel, pid, did), 0, 0));
+}
+clComplexToMagPhase::sptr clComplexToMagPhase::make(int plat, int sel, int pid, int did, int)
+{
+    return gnuradio::get_initial_sptr(new clComplexToMagPhase_impl(pick_device(plat, sel, pid, did)));
+}
+clMagPhaseToComplex::sptr clMagPhaseToComplex::make(int plat, int sel, int pid, int did, int)
+{
+    return gnuradio::get_initial_sptr(new clMagPhaseToComplex_impl(pick_device(plat, sel, pid, did)));
+}
+clFFT::sptr clFFT::make(int fftSize, int dir, const std::vector<float> &window, int idataType, int plat, int sel,
+                        int pid, int did, int, int num_streams, bool shift)
+{
+    return gnuradio::get_initial_sptr(
+        new clFFT_impl(fftSize, dir, window, idataType, pick_device(plat, sel, pid, did), num_streams, shift));
+}
+clFilter::sptr clFilter::make(int plat, int sel, int pid, int did, int decimation, const std::vector<float> &taps,
+                              int nthreads, int, bool use_time)
+{
+    return gnuradio::get_initial_sptr(new clFilter_impl(pick_device(plat, sel, pid, did), decimation, taps, nthreads, use_time));
+}
+clPolyphaseChannelizer::sptr clPolyphaseChannelizer::make(int plat, int sel, int pid, int did,
+                                                          const std::vector<float> &taps, int buf_items,
+                                                          int num_channels, int ninputs_per_iter,
+                                                          const std::vector<int> &ch_map, int)
+{
+    return gnuradio::get_initial_sptr(new clPolyphaseChannelizer_impl(pick_device(plat, sel, pid, did), taps, buf_items,
+                                                                      num_channels, ninputs_per_iter, ch_map));
+}
+clXEngine::sptr clXEngine::make(int plat, int sel, int pid, int did, bool, int data_type, int polarization,
+                                int num_inputs, int, int, int num_channels, int integration,
+                                std::vector<std::string>, bool, std::string, int, bool, long, std::string, double,
+                                double, bool disable_output, int pipeline_integration)
+{
+    return gnuradio::get_initial_sptr(new clXEngine_impl(pick_device(plat, sel, pid, did), data_type, polarization,
+                                                         num_inputs, num_channels, integration, disable_output,
+                                                         pipeline_integration));
+}
+
+} // namespace clenabled
+} // namespace gr

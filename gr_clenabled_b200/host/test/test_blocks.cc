@@ -1,0 +1,159 @@
+// Drives the gr::clenabled block classes the way the reference's CLI tools do
+// (lib/test_clenabled.cc instantiates the _impl classes directly and calls the work
+// functions, no scheduler): make(), work()/general_work(), known answers.
+#include <clenabled/blocks.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+using namespace gr::clenabled;
+static int failures = 0;
+#define CHECK(cond)                                                                     \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);                      \
+            failures++;                                                                 \
+        }                                                                               \
+    } while (0)
+
+template <class E, class F>
+bool throws(F f)
+{
+    try {
+        f();
+    } catch (const E &) {
+        return true;
+    } catch (...) {
+        return false;
+    }
+    return false;
+}
+
+int main()
+{
+    const int GPU = OCLTYPE_GPU, FIRST = OCLDEVICESELECTOR_FIRST;
+    // --- Multiply Const: (1.0, 0.5) * 2 = (2.0, 1.0)   (test_clenabled.cc:1193,1336,1351-1352)
+    {
+        auto blk = clMathConst::make(DTYPE_COMPLEX, GPU, FIRST, 0, 0, 2.0f, MATHOP_MULTIPLY);
+        std::vector<gr_complex> in(8192, gr_complex(1.0f, 0.5f)), out(8192);
+        gr_vector_const_void_star iv{in.data()};
+        gr_vector_void_star ov{out.data()};
+        CHECK(blk->work(8192, iv, ov) == 8192);
+        bool ok = true;
+        for (auto &v : out) ok = ok && v == gr_complex(2.0f, 1.0f);
+        CHECK(ok);
+        blk->set_k(3.0f);
+        CHECK(blk->k() == 3.0f);
+        CHECK(blk->output_multiple() > 0);
+    }
+    // --- Multiply (2 -> 1)
+    {
+        auto blk = clMathOp::make(DTYPE_COMPLEX, GPU, FIRST, 0, 0, MATHOP_MULTIPLY_CONJUGATE);
+        std::vector<gr_complex> a(1000, gr_complex(1.0f, 2.0f)), b(1000, gr_complex(3.0f, -1.0f)), c(1000);
+        gr_vector_const_void_star iv{a.data(), b.data()};
+        gr_vector_void_star ov{c.data()};
+        CHECK(blk->work(1000, iv, ov) == 1000);
+        CHECK(c[0] == gr_complex(1.0f, 2.0f) * std::conj(gr_complex(3.0f, -1.0f)));
+        CHECK(blk->work(0, iv, ov) == 0);
+    }
+    // --- FFT: the tone of test_clenabled.cc:835-851 is i*e^{-2 pi i n/N}: one bin, i*N at N-1
+    {
+        const int N = 8192, nvec = 3;
+        auto blk = clFFT::make(N, CLFFT_FORWARD_DIR, std::vector<float>(), DTYPE_COMPLEX, GPU, FIRST, 0, 0, 0, 1, false);
+        std::vector<gr_complex> in(N * nvec), out(N * nvec);
+        for (int v = 0; v < nvec; v++)
+            for (int i = 0; i < N; i++)
+                in[v * N + i] = gr_complex((float)sin(2 * M_PI * i / N), (float)cos(2 * M_PI * i / N));
+        gr_vector_const_void_star iv{in.data()};
+        gr_vector_void_star ov{out.data()};
+        CHECK(blk->work(nvec, iv, ov) == nvec);        // items are vectors
+        double worst = 0;
+        for (int v = 0; v < nvec; v++)
+            for (int i = 0; i < N; i++) {
+                gr_complex want = (i == N - 1) ? gr_complex(0.0f, (float)N) : gr_complex(0, 0);
+                worst = std::max(worst, (double)std::abs(out[v * N + i] - want));
+            }
+        CHECK(worst < 1e-5 * N);
+        CHECK(throws<std::runtime_error>([&] {
+            clFFT::make(N, CLFFT_FORWARD_DIR, std::vector<float>(100, 1.0f), DTYPE_COMPLEX, GPU, FIRST, 0, 0);
+        }));
+    }
+    // --- Filter: impulse response = taps, both kernels; decimation; tap swap
+    for (int use_time = 0; use_time < 2; use_time++) {
+        std::vector<float> taps(256);
+        for (int i = 0; i < 256; i++) taps[i] = i / 1000.0f;            // test-clfilter.cc:98-100
+        auto blk = clFilter::make(GPU, FIRST, 0, 0, 1, taps, 1, 0, use_time != 0);
+        std::vector<gr_complex> in(8192, gr_complex(0, 0)), out(8192);
+        in[0] = gr_complex(1.0f, 0.0f);
+        gr_vector_const_void_star iv{in.data()};
+        gr_vector_void_star ov{out.data()};
+        CHECK(blk->work(8192, iv, ov) == 8192);
+        double worst = 0;
+        for (int i = 0; i < 8192; i++) worst = std::max(worst, (double)std::abs(out[i] - gr_complex(i < 256 ? taps[i] : 0.0f, 0.0f)));
+        CHECK(worst < 1e-5);
+        CHECK(blk->taps().size() == 256);
+        auto dec = clFilter::make(GPU, FIRST, 0, 0, 4, taps, 1, 0, use_time != 0);
+        CHECK(dec->decimation() == 4);
+        CHECK(dec->work(2048, iv, ov) == 2048);        // consumes 8192, produces 2048
+        CHECK(std::abs(out[1] - gr_complex(taps[4], 0)) < 1e-5);
+    }
+    // --- Polyphase channelizer: item accounting of general_work
+    {
+        const int M = 64, T = 128, buf = 4096;
+        std::vector<float> taps(T, 1.0f / T);
+        std::vector<int> map{5, 0, 63};
+        auto blk = clPolyphaseChannelizer::make(GPU, FIRST, 0, 0, taps, buf, M, M, map);
+        CHECK(blk->history() == (unsigned)T);
+        CHECK(blk->output_multiple() == 3 * buf / M);
+        std::vector<gr_complex> in(buf + T, gr_complex(1.0f, 0.0f)), out(3 * buf / M);
+        gr_vector_int ni{(int)in.size()};
+        gr_vector_const_void_star iv{in.data()};
+        gr_vector_void_star ov{out.data()};
+        CHECK(blk->general_work(3 * buf / M, ni, iv, ov) == 3 * buf / M);
+        CHECK(blk->consumed_each() == buf);
+        // DC input: all energy in channel 0 = sum(taps) * ... = 1 per arm * M arms / M
+        CHECK(std::abs(out[1] - gr_complex(1.0f, 0.0f)) < 1e-4 && std::abs(out[0]) < 1e-4 && std::abs(out[2]) < 1e-4);
+        CHECK(throws<std::invalid_argument>([&] { clPolyphaseChannelizer::make(GPU, FIRST, 0, 0, taps, 100, M, M, map); }));
+    }
+    // --- X-engine: two polarisations through the stream ports, PDU out
+    {
+        const int A = 4, F = 8, T = 64, npol = 2;
+        auto blk = clXEngine::make(GPU, FIRST, 0, 0, false, DTYPE_BYTE, npol, A, 1, 0, F, T, {});
+        std::vector<std::vector<signed char>> ports(A * npol, std::vector<signed char>((size_t)T * F * 2));
+        unsigned seed = 1;
+        for (auto &p : ports)
+            for (auto &v : p) {
+                seed = seed * 1664525u + 1013904223u;
+                v = (signed char)((int)(seed >> 24) % 100 - 50);
+            }
+        gr_vector_const_void_star iv;
+        for (auto &p : ports) iv.push_back(p.data());
+        gr_vector_int ni(A * npol, T);
+        gr_vector_void_star ov;
+        CHECK(blk->general_work(40, ni, iv, ov) == 40);          // partial integration: no PDU yet
+        CHECK(blk->published("xcorr").empty());
+        gr_vector_const_void_star iv2;
+        for (auto &p : ports) iv2.push_back(p.data() + 40 * F * 2);
+        CHECK(blk->general_work(1000, ni, iv2, ov) == 24);       // only what completes the integration
+        auto &msgs = blk->published("xcorr");
+        CHECK(msgs.size() == 1);
+        if (msgs.size() == 1) {
+            CHECK(pmt::symbol_to_string(pmt::car(msgs[0])) == "triang_matrix");
+            const auto &m = pmt::c32vector_elements(pmt::cdr(msgs[0]));
+            CHECK((int)m.size() == F * (A * (A + 1) / 2) * npol * npol);
+            // baseline (0,0), XX of channel 0 = sum |x|^2 / 127^2, imaginary part 0
+            double p = 0;
+            for (int t = 0; t < T; t++) {
+                double re = ports[0][(size_t)t * F * 2], im = ports[0][(size_t)t * F * 2 + 1];
+                p += re * re + im * im;
+            }
+            CHECK(std::abs(m[0].real() - p / (127.0 * 127.0)) < 1e-4 * p / (127.0 * 127.0) + 1e-6);
+            CHECK(m[0].imag() == 0.0f);
+        }
+        CHECK(throws<std::out_of_range>([&] { clXEngine::make(GPU, FIRST, 0, 0, false, DTYPE_BYTE, 1, 1, 1, 0, F, T, {}); }));
+    }
+    if (failures == 0) printf("ALL OK\n");
+    return failures == 0 ? 0 : 1;
+}

@@ -1,0 +1,52 @@
+"""Summarise an .ncu-rep (one kernel) into the handful of numbers DESIGN.md / bench.py cite.
+usage: ncu_summary.py <rep> [units-per-launch for the opcode histogram]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "sm__inst_executed.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum", "sm__cycles_elapsed.max",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        print("kernel: %s" % name)
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print("  %-68s %14s %s" % (k, vals[i], units[i]))
+        st = []
+        for i, h in enumerate(hdr):
+            if "issue_stalled" in h and h.endswith("_per_issue_active.ratio"):
+                try:
+                    st.append((float(vals[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+                except ValueError:
+                    pass
+        print("  top stalls (warps per issue): " + ", ".join("%s %.2f" % (n, v) for v, n in sorted(st, reverse=True)[:6]))
+        rd = float(vals[hdr.index("dram__bytes_read.sum")]) if "dram__bytes_read.sum" in hdr else 0
+        wr = float(vals[hdr.index("dram__bytes_write.sum")]) if "dram__bytes_write.sum" in hdr else 0
+        print("  dram traffic (read+write): %.3f %s" % (rd + wr, units[hdr.index("dram__bytes_read.sum")]))
+
+
+if __name__ == "__main__":
+    main()
