@@ -325,6 +325,38 @@ def main():
     del hx, hy
 
     extra = {}
+    if world > 1 and not args.no_blocks:
+        # clXEngine sharded by channel: every rank correlates its slab, the slabs meet
+        # in one NCCL all_gather; device-resident slabs, 4 rotating buffers per rank
+        from gr_clenabled_b200 import multigpu
+        del x, y
+        torch.cuda.empty_cache()
+        A, F, T = 32, 1024, 1024
+        f0, fc = multigpu.shard_channels(F, rank, world)
+        nbl = A * (A + 1) // 2
+        bufs = [torch.randint(-127, 128, (T * A * fc * 2,), dtype=torch.int8, device="cuda") for _ in range(4)]
+        slab = torch.empty(fc * nbl * 2, dtype=torch.float32, device="cuda")
+        xe = blocks.clXEngine(1, 2, 0, local, False, capi.DTYPE_BYTE, 1, A, 1, 0, fc, T, [])
+        def xstep(i):
+            xe.launch_device(bufs[i % 4].data_ptr(), slab.data_ptr(), False, sp)
+            return multigpu.gather_visibilities(slab, F, nbl * 2)
+        for i in range(3):
+            full = xstep(i)
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        nx = 10
+        for i in range(nx):
+            full = xstep(i)
+        x1.record(stream)
+        barrier()
+        t = torch.tensor([x0.elapsed_time(x1) / nx], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item()) * 1e3
+        extra["clXEngine_32st_1024ch_int1024_sharded"] = {
+            "us_per_integration": us, "Msamples_s": A * F * T / us, "gpus": world,
+            "collective": "all_gather of %d B visibility slabs per rank (NCCL)" % (slab.numel() * 4),
+            "gathered_items": int(full.numel() // 2)}
     if rank == 0 and world == 1 and not args.no_blocks:
         del x, y
         torch.cuda.empty_cache()
