@@ -131,7 +131,7 @@ def run_reference(args, rank):
     cores = os.cpu_count() or 1
     orc.lib().orc_set_threads(cores)
     threads = orc.lib().orc_num_threads()
-    nvec = 2048                                            # bounded sample: 16 Mi samples per step
+    nvec = args.nvec                                       # the same batch per step as our arm (8192 vectors)
     import numpy as np
     x = orc.rng_c32(FFT_N * nvec, orc.SEED_F)
     for _ in range(max(1, min(args.warmup, 3))):
@@ -365,8 +365,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v1, _ = cpu_fft_run(512, 2, 1)
-        reps = 4
+        _, d1 = cpu_fft_run(512, 1, 1)
+        v1, _ = cpu_fft_run(512, max(1, int(4.0 / max(d1, 1e-3))), 1)      # ~4 s on one thread
+        _, dN = cpu_fft_run(2048, 1, cores)
+        reps = max(2, int(10.0 / max(dN, 1e-3)))                            # ~10 s on all threads
         vN, dtN = cpu_fft_run(2048, reps, cores)
         cpu = {"value": vN, "unit": "Msamples/s", "cores": cores, "kind": "port",
                "single_thread_value": v1,
