@@ -183,8 +183,11 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
 }
 
 // pick a chunk (in items) whose largest port moves about `target` bytes
-inline long chunk_for(const PortDesc &pd, size_t target = (size_t)8 << 20)
+size_t chunk_target_bytes();     // default 32 MiB, CLB200_CHUNK_MB overrides (tuning)
+
+inline long chunk_for(const PortDesc &pd, size_t target = 0)
 {
+    if (target == 0) target = chunk_target_bytes();
     size_t mx = 1;
     for (int k = 0; k < pd.nin; k++) mx = std::max(mx, pd.in_bytes[k]);
     for (int k = 0; k < pd.nout; k++) mx = std::max(mx, pd.out_bytes[k]);

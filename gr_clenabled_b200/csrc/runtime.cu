@@ -2,6 +2,7 @@
 // Replaces GRCLBase::InitOpenCL / cleanup (lib/GRCLBase.cpp:17-369, :423-483).
 #include "common.cuh"
 #include <cstdarg>
+#include <cstdlib>
 
 namespace clb200 {
 
@@ -27,6 +28,17 @@ int device_sm_count(int device)
         cache[device] = v;
     }
     return cache[device];
+}
+
+size_t chunk_target_bytes()
+{
+    static size_t v = 0;
+    if (v == 0) {
+        const char *e = getenv("CLB200_CHUNK_MB");
+        long mb = e ? atol(e) : 32;       // 32 MiB: best PCIe overlap measured on B200 (tools/e2e_fft.py)
+        v = (size_t)(mb >= 1 && mb <= 1024 ? mb : 32) << 20;
+    }
+    return v;
 }
 
 int Buf::reserve(size_t bytes)
