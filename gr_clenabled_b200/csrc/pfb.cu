@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "fft_device.cuh"
 #include <cmath>
+#include <cstdlib>
 
 using namespace clb200;
 using namespace clb200::fftdev;
@@ -47,18 +48,29 @@ k_pfb(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
         if (active) {
             const int rot = (int)((i * (long)rot_step) & (M - 1));
             const float2 *xin = in + i * (long)R + (ntaps - 1);      // in[i*R - k + T-1]
+            // tap loop outside, arm loop (unrolled) inside: EPT independent loads in flight
+            // per step; each arm still accumulates in ascending k like the reference (:163)
+            int j[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; e++) {
-                const int slot = in_index<P, EPT>(lt, e);
-                const int j = (slot - rot) & (M - 1);
-                float re = 0.f, im = 0.f;
-                for (int k = j; k < ntaps; k += M) {
-                    const float2 v = __ldg(xin - k);
-                    const float t = __ldg(taps + k);
-                    re = fmaf(v.x, t, re);
-                    im = fmaf(v.y, t, im);
+                j[e] = (in_index<P, EPT>(lt, e) - rot) & (M - 1);
+                x[e] = make_float2(0.f, 0.f);
+            }
+            for (int k0 = 0; k0 < ntaps; k0 += M) {
+                float2 v[EPT];
+                float t[EPT];
+#pragma unroll
+                for (int e = 0; e < EPT; e++) {
+                    const int k = k0 + j[e];
+                    const bool ok = k < ntaps;
+                    v[e] = ok ? __ldg(xin - k) : make_float2(0.f, 0.f);
+                    t[e] = ok ? __ldg(taps + k) : 0.f;
                 }
-                x[e] = make_float2(im, re);          // re/im swapped: inverse via forward core
+#pragma unroll
+                for (int e = 0; e < EPT; e++) {      // x holds (im, re): inverse via the forward core
+                    x[e].y = fmaf(v[e].x, t[e], x[e].y);
+                    x[e].x = fmaf(v[e].y, t[e], x[e].x);
+                }
             }
         } else {
 #pragma unroll
@@ -122,9 +134,11 @@ PfbVariant make_pfb()
 const PfbVariant *pick_pfb(int logm)
 {
     static const PfbVariant tab[] = {
-        make_pfb<1, 2, 128, 4>(),  make_pfb<2, 4, 128, 4>(),  make_pfb<3, 8, 128, 4>(),
-        make_pfb<4, 4, 32, 4>(),   make_pfb<5, 8, 32, 4>(),   make_pfb<6, 8, 32, 4>(),
-        make_pfb<7, 8, 16, 4>(),   make_pfb<8, 16, 16, 2>(),  make_pfb<9, 8, 4, 4>(),
+        // up to 128 channels: one-warp CTAs (barriers are free, many CTAs hide the load
+        // latency) -- measured best for 64 channels: 4.36 TB/s vs 3.67 with 256 threads
+        make_pfb<1, 2, 32, 24>(),  make_pfb<2, 4, 32, 24>(),  make_pfb<3, 8, 32, 16>(),
+        make_pfb<4, 4, 8, 24>(),   make_pfb<5, 8, 8, 24>(),   make_pfb<6, 8, 4, 24>(),
+        make_pfb<7, 8, 2, 24>(),   make_pfb<8, 16, 16, 2>(),  make_pfb<9, 8, 4, 4>(),
         make_pfb<10, 16, 4, 2>(),  make_pfb<11, 16, 2, 2>(),  make_pfb<12, 16, 1, 2>(),
     };
     if (logm < 1 || logm > 12) return nullptr;
