@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "fft_device.cuh"      // static_for
 #include <cmath>
+#include <cstdlib>
 
 using namespace clb200;
 using clb200::fftdev::static_for;
@@ -339,6 +340,15 @@ __global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_i8(XeParams p)
     }
 }
 
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+} // namespace
+#include "xengine_tc.cuh"
+namespace {
+
 // packed 4-bit (hi nibble re, lo nibble im) -> int8 pairs; LUT of CharToComplex (:833)
 __global__ void k_unpack4(const uint8_t *__restrict__ in, int8_t *__restrict__ out, long n)
 {
@@ -428,6 +438,7 @@ struct XEngine : clb200_block {
     int data_type = 0, npol = 1, A = 0, F = 0, T = 0;
     int Ftotal = 0, f_first = 0;       // channel shard within the caller's buffer
     const XeVariant *var = nullptr;
+    bool use_tc = false;
     Buf d_in[2], d_unpacked, d_acc, d_out;
     Buf pin_in[2], pin_out;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -487,7 +498,9 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         scale = 1.0f / 49.0f;
     }
     const XeVariant *v = x->var;
-    const int ngroups = (x->F + v->fc - 1) / v->fc;
+    const bool tc = x->use_tc;                         // tcgen05/TMEM kernel (<= 32 rows of inputs)
+    const int fc = tc ? TC_FC : v->fc;
+    const int ngroups = (x->F + fc - 1) / fc;
     // fewer channel groups than ~2 waves of CTAs: split the integrations over time as well
     const int nst = (T + XE_TT - 1) / XE_TT;
     const bool split = ngroups < 2 * sms && nst > 1;
@@ -518,7 +531,12 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.scale = scale;
     long rowb = (long)Fstride * x->npol * 2;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
-    v->kernel[x->npol - 1]<<<grid, XE_THREADS, v->smem_bytes, st>>>(p);
+    if (tc) {
+        if (x->npol == 1) k_xengine_tc<1><<<grid, XE_THREADS, TC_SMEM, st>>>(p);
+        else k_xengine_tc<2><<<grid, XE_THREADS, TC_SMEM, st>>>(p);
+    } else {
+        v->kernel[x->npol - 1]<<<grid, XE_THREADS, v->smem_bytes, st>>>(p);
+    }
     CLB_CUDA(cudaGetLastError());
     x->n_launch++;
     if (nslice > 1 && out_f32 != nullptr) {
@@ -659,6 +677,15 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
     cudaError_t e = cudaFuncSetAttribute((const void *)x->var->kernel[npol - 1],
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          x->var->smem_bytes);
+    if (e == cudaSuccess && num_inputs * npol <= 32) {
+        const char *legacy = getenv("CLB200_XE_LEGACY");       // force the mma.sync kernel (A/B testing)
+        x->use_tc = !(legacy && atoi(legacy));
+        if (x->use_tc)
+            e = npol == 1 ? cudaFuncSetAttribute((const void *)k_xengine_tc<1>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
+                          : cudaFuncSetAttribute((const void *)k_xengine_tc<2>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    }
     if (e != cudaSuccess) {
         set_error("clXEngine: cannot reserve %d B of shared memory: %s", x->var->smem_bytes,
                   cudaGetErrorString(e));
