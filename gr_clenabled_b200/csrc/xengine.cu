@@ -532,8 +532,8 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     long rowb = (long)Fstride * x->npol * 2;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
     if (tc) {
-        if (x->npol == 1) k_xengine_tc<1><<<grid, XE_THREADS, TC_SMEM, st>>>(p);
-        else k_xengine_tc<2><<<grid, XE_THREADS, TC_SMEM, st>>>(p);
+        if (x->npol == 1) k_xengine_tc<1><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
+        else k_xengine_tc<2><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
     } else {
         v->kernel[x->npol - 1]<<<grid, XE_THREADS, v->smem_bytes, st>>>(p);
     }

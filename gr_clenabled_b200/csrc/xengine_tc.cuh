@@ -26,7 +26,8 @@ namespace {
 constexpr int TC_FC = 16;                    // channels per CTA
 constexpr int TC_CS = 2048 + 16;             // bytes per channel image; +16 spreads the STS banks
 constexpr int TC_ZB = TC_FC * TC_CS;         // bytes per stage buffer
-constexpr int TC_SMEM = 2 * TC_ZB + 64;      // + 2 mbarriers + TMEM base slot
+constexpr int TC_SMEM = 2 * TC_ZB + 64;      // + 5 mbarriers + TMEM base slot
+constexpr int TC_THREADS = XE_THREADS + 32;  // 16 feed/epilogue warps + 1 MMA warp
 
 // instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 64, M = 64
 constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
@@ -55,9 +56,13 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_mbar_init(uint64_t *bar)
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, int count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -86,7 +91,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
 }
 
 template <int NPOL>
-__global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_tc(XeParams p)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_xengine_tc(XeParams p)
 {
     constexpr int FC = TC_FC;
     constexpr int ASTN = 32 / NPOL;                          // stations per stage image (padded)
@@ -98,8 +103,10 @@ __global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_tc(XeParams p)
     constexpr int ZBD = (NPOL == 1) ? TC_CS : 32;
 
     extern __shared__ __align__(128) uint8_t tc_smem[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(tc_smem + 2 * TC_ZB);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2);
+    uint64_t *full = reinterpret_cast<uint64_t *>(tc_smem + 2 * TC_ZB);     // [2]
+    uint64_t *empty = full + 2;                                              // [2]
+    uint64_t *tfree = full + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nbl = p.A * (p.A + 1) / 2;
@@ -126,8 +133,11 @@ __global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_tc(XeParams p)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (threadIdx.x == 0) {
-        tc_mbar_init(&mbar[0]);
-        tc_mbar_init(&mbar[1]);
+        tc_mbar_init(&full[0], XE_WARPS);
+        tc_mbar_init(&full[1], XE_WARPS);
+        tc_mbar_init(&empty[0], 1);
+        tc_mbar_init(&empty[1], 1);
+        tc_mbar_init(tfree, XE_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -216,55 +226,57 @@ __global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_tc(XeParams p)
         }
     };
 
-    uint32_t pre0[QPT][4], pre1[QPT][4];            // stages s0+even / s0+odd in flight
-    load_stage(s0, pre0);
-    if (s0 + 1 < s1) load_stage(s0 + 1, pre1);
-    store_stage(tc_smem, pre0);
-    if (s0 + 2 < s1) load_stage(s0 + 2, pre0);
-    fence_proxy_async_smem();
-    __syncthreads();
-
-    uint32_t parity[2] = {0, 0};
-    bool pending[2] = {false, false};               // a commit on mbar[b] not yet waited for
+    // ---- warp-specialised pipeline -------------------------------------------------
+    //   warps 0..15 : feed (global -> registers -> transposed K-major image) + epilogue
+    //   warp 16     : one lane issues the UMMAs
+    //   full[b]  (16 arrivals)  : stage image b is complete and visible to the tensor core
+    //   empty[b] (tcgen05.commit): the MMAs that read image b -- and all earlier ones -- are done
+    //   tfree    (16 arrivals)  : the epilogue has drained TMEM, a new group may overwrite it
+    const int nstages = s1 - s0;
     const uint32_t zaddr = (uint32_t)__cvta_generic_to_shared(tc_smem);
 
-    for (int sg = s0; sg < s1; sg++) {
-        const int b = (sg - s0) & 1;
-        const bool group_first = (sg == s0) || (sg % nst == 0);
-        if (threadIdx.x == 0) {
-            tc_fence_after();
+    if (warp == XE_WARPS) {
+        if (lane == 0) {
+            int groups_done = 0;
+            for (int n = 0; n < nstages; n++) {
+                const int sg = s0 + n, b = n & 1;
+                const bool group_first = (n == 0) || (sg % nst == 0);
+                tc_mbar_wait(&full[b], (uint32_t)(n >> 1) & 1u);
+                if (group_first && n > 0) {
+                    tc_mbar_wait(tfree, (uint32_t)(groups_done - 1) & 1u);
+                }
+                tc_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < FC; ch++) {
-                const uint64_t d = tc_smem_desc(zaddr + b * TC_ZB + ch * TC_CS);
-                tc_mma_i8(tmem_base + (((uint32_t)(ch & 1) * 16u) << 16) + (uint32_t)(ch >> 1) * 64u, d, d,
-                          group_first ? 0u : 1u);
+                for (int ch = 0; ch < FC; ch++) {
+                    const uint64_t d = tc_smem_desc(zaddr + b * TC_ZB + ch * TC_CS);
+                    tc_mma_i8(tmem_base + (((uint32_t)(ch & 1) * 16u) << 16) + (uint32_t)(ch >> 1) * 64u, d, d,
+                              group_first ? 0u : 1u);
+                }
+                tc_commit(&empty[b]);
+                if ((n + 1 == nstages) || ((sg + 1) % nst == 0)) groups_done++;
             }
-            tc_commit(&mbar[b]);
         }
-        pending[b] = true;
-
-        // feed: stage sg+1 into the other buffer once the MMAs that read it are done
-        if (sg + 1 < s1) {
-            if (pending[b ^ 1]) {
-                tc_mbar_wait(&mbar[b ^ 1], parity[b ^ 1]);
-                parity[b ^ 1] ^= 1;
-                pending[b ^ 1] = false;
-            }
+    } else {
+        uint32_t pre0[QPT][4], pre1[QPT][4];        // stages n even / n odd, two stages ahead
+        load_stage(s0, pre0);
+        if (nstages > 1) load_stage(s0 + 1, pre1);
+        for (int n = 0; n < nstages; n++) {
+            const int sg = s0 + n, b = n & 1;
+            if (n >= 2) tc_mbar_wait(&empty[b], (uint32_t)((n >> 1) - 1) & 1u);   // MMAs of stage n-2 are done
             if (b == 0) {
-                store_stage(tc_smem + TC_ZB, pre1);
-                if (sg + 3 < s1) load_stage(sg + 3, pre1);
-            } else {
                 store_stage(tc_smem, pre0);
-                if (sg + 3 < s1) load_stage(sg + 3, pre0);
+                if (n + 2 < nstages) load_stage(sg + 2, pre0);
+            } else {
+                store_stage(tc_smem + TC_ZB, pre1);
+                if (n + 2 < nstages) load_stage(sg + 2, pre1);
             }
             fence_proxy_async_smem();
-        }
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&full[b]);
 
-        const bool group_done = (sg + 1 == s1) || ((sg + 1) % nst == 0);
-        if (group_done) {
-            tc_mbar_wait(&mbar[b], parity[b]);        // every MMA of the group has landed in TMEM
-            parity[b] ^= 1;
-            pending[b] = false;
+            const bool group_done = (n + 1 == nstages) || ((sg + 1) % nst == 0);
+            if (!group_done) continue;
+            tc_mbar_wait(&empty[b], (uint32_t)(n >> 1) & 1u);       // every MMA of the group has landed
             tc_fence_after();
             const int f0 = (sg / nst) * FC;
             const int wq = warp & 3;
@@ -309,9 +321,12 @@ __global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_tc(XeParams p)
                 }
             }
             tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(tfree);
         }
-        __syncthreads();
     }
+    tc_fence_before();
+    __syncthreads();
 
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
