@@ -53,6 +53,8 @@ struct XeParams {
     int A, npol, F, Fstride, f_off, T;
     int accumulate;         // out += result
     int split;              // CTAs share channel groups: partial sums meet through int32 atomics
+    int nslice;             // > 0: time-sliced decomposition, grid = groups x nslice
+    int l2_rows;            // prefetch whole (t, station) rows into L2 ahead of the demand loads
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
 };
@@ -139,7 +141,15 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     // int32 result with atomics (p.split); otherwise every CTA owns whole groups.
     const int nst = (p.T + XE_TT - 1) / XE_TT;
     int s0, s1;                                   // ngroups * nst < 2^31 (checked on the host)
-    if (p.split) {
+    if (p.nslice > 0) {
+        // time-sliced: CTA = (slice, channel group), groups fastest, one wave.  CTAs that run
+        // together read neighbouring 32 B runs of the SAME (t, station) rows at about the same
+        // time, which is what lets the DRAM controllers serve them from open pages.
+        const int grp = blockIdx.x % ngroups, sl = blockIdx.x / ngroups;
+        const int len = (nst + p.nslice - 1) / p.nslice;
+        s0 = grp * nst + sl * len;
+        s1 = min(grp * nst + nst, s0 + len);
+    } else if (p.split) {
         const long total = (long)ngroups * nst;
         s0 = (int)(total * blockIdx.x / gridDim.x);
         s1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
@@ -503,9 +513,17 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     const int ngroups = (x->F + fc - 1) / fc;
     // fewer channel groups than ~2 waves of CTAs: split the integrations over time as well
     const int nst = (T + XE_TT - 1) / XE_TT;
-    const bool split = ngroups < 2 * sms && nst > 1;
+    // few channel groups: one wave of (slice, group) CTAs; many: whole groups per CTA
+    int tslices = 0;
+    if (ngroups < sms && nst > 1) tslices = std::min(nst, std::max(1, sms / ngroups));
+    {
+        const char *e = getenv("CLB200_XE_SLICES");       // tuning override: 0 = stream-K split
+        if (e && ngroups < 2 * sms && nst > 1) tslices = std::min(nst, atoi(e));
+    }
+    const bool split = (tslices > 1) || (tslices == 0 && ngroups < 2 * sms && nst > 1);
     const int nslice = split ? 2 : 1;
-    const int grid = (int)std::min<long>(sms, split ? (long)ngroups * nst : ngroups);
+    const int grid = tslices > 0 ? ngroups * tslices
+                                 : (int)std::min<long>(sms, split ? (long)ngroups * nst : ngroups);
     const long nout = x->out_items();
     if (nslice > 1) {
         // partial sums meet in an int32 buffer through atomics
@@ -521,6 +539,11 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.out_i32 = (nslice > 1 && out_i32 == nullptr) ? (int32_t *)x->d_acc.p : out_i32;
     p.out_f32 = out_f32;
     p.split = split ? 1 : 0;
+    p.nslice = tslices;
+    {
+        const char *e = getenv("CLB200_XE_L2ROWS");
+        p.l2_rows = e ? atoi(e) : 0;      // measured slower on B200 (50.9 vs 44.7 us): off by default
+    }
     p.A = x->A;
     p.npol = x->npol;
     p.F = x->F;

@@ -116,7 +116,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_xengine_tc(XeParams p)
     const int nst = (p.T + XE_TT - 1) / XE_TT;
 
     int s0, s1;
-    if (p.split) {
+    if (p.nslice > 0) {
+        // time-sliced: CTA = (slice, channel group), groups fastest, one wave.  CTAs that run
+        // together read neighbouring 32 B runs of the SAME (t, station) rows at about the same
+        // time, which is what lets the DRAM controllers serve them from open pages.
+        const int grp = blockIdx.x % ngroups, sl = blockIdx.x / ngroups;
+        const int len = (nst + p.nslice - 1) / p.nslice;
+        s0 = grp * nst + sl * len;
+        s1 = min(grp * nst + nst, s0 + len);
+    } else if (p.split) {
         const long total = (long)ngroups * nst;
         s0 = (int)(total * blockIdx.x / gridDim.x);
         s1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
@@ -260,8 +268,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_xengine_tc(XeParams p)
         uint32_t pre0[QPT][4], pre1[QPT][4];        // stages n even / n odd, two stages ahead
         load_stage(s0, pre0);
         if (nstages > 1) load_stage(s0 + 1, pre1);
+        // Whole-row L2 prefetch (time-sliced mode): the CTAs of a slice walk the same
+        // (t, station) rows; each one asks L2 for a share of the COMPLETE rows (all
+        // channels) of the stage PF_AHEAD steps ahead, so DRAM sees row-sized bursts and the
+        // 32 B demand loads of every CTA find their sectors in L2.
+        constexpr int PF_AHEAD = 3;
+        const bool do_pf = p.l2_rows && p.nslice > 0 && (rowb % 16 == 0);
+        const int rows_per_stage = XE_TT * p.A;
+        const int pf_share = (rows_per_stage + ngroups - 1) / ngroups;
         for (int n = 0; n < nstages; n++) {
             const int sg = s0 + n, b = n & 1;
+            if (do_pf && n + PF_AHEAD < nstages && (int)threadIdx.x < pf_share) {
+                const int grp = sg / nst, st = sg - grp * nst + PF_AHEAD;
+                const int r = grp * pf_share + threadIdx.x;             // row of that stage: (t, station)
+                const int t = st * XE_TT + r / p.A;
+                if (r < rows_per_stage && t < p.T) {
+                    const int8_t *row = p.in + ((long)t * p.A + (r % p.A)) * rowb;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((uint32_t)rowb) : "memory");
+                }
+            }
             if (n >= 2) tc_mbar_wait(&empty[b], (uint32_t)((n >> 1) - 1) & 1u);   // MMAs of stage n-2 are done
             if (b == 0) {
                 store_stage(tc_smem, pre0);
