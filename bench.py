@@ -56,6 +56,17 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(nvec):
+    """dram bytes per launch of the FFT kernel from the committed ncu --set full capture
+    (profiles/r1_traffic.json); only valid for the launch shape that was captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["k_fft_8192pt_x8192vec"]
+        return t["bytes"] if nvec == 8192 else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled during the timed region."""
 
@@ -386,7 +397,7 @@ def main():
                        "l2": "inputs larger than L2 (2 x %d MiB per step), no flush needed" % (nsamp * 8 >> 20),
                        "parallelism": "vectors sharded over %d GPU(s), no collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": ncu_traffic(nvec), "peak_source": peak_src,
                          "kernel": "k_fft<13,...>", "bytes_per_launch": BYTES_PER_SAMPLE * nsamp},
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": nsamp * 8,
                     "d2h_bytes_per_step": nsamp * 8, "steps": e2e_steps,
