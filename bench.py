@@ -238,6 +238,37 @@ def secondary_blocks(torch, blocks, capi, dev, stream_ptr, hbm_peak):
     return out
 
 
+def per_call(blocks, capi, dev, n=8192, iters=300):
+    """BASELINE configs[0]: scheduler-sized work() calls (8192 gr_complex, pageable host buffers,
+    1 warm-up + N timed calls like lib/test_clenabled.cc:1237-1251), through the C ABI."""
+    import numpy as np
+    from oracle import oracle as orc
+    lib = capi.load()
+    x = orc.rng_c32(n, orc.SEED_M)
+    out = np.zeros(n, np.complex64)
+    xp, op = C.c_void_p(x.ctypes.data), C.c_void_p(out.ctypes.data)
+    res = {}
+    mc = blocks.clMathConst(capi.DTYPE_COMPLEX, 1, 2, 0, dev, 2.0, capi.OP_MULTIPLY)
+    ff = blocks.clFFT(n, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, 1, 2, 0, dev)
+    for name, fn in (("clMultiplyConst", lambda: lib.clb200_mathconst_work(mc._h, xp, op, n)),
+                     ("clFFT_8192", lambda: lib.clb200_fft_work(ff._h, xp, op, 1))):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        dt = (time.perf_counter() - t0) / iters
+        res[name] = {"us_per_call": dt * 1e6, "Msamples_s": n / dt / 1e6}
+    # the reference CPU loop on the same buffer (clMathConst_impl::testCPU, 1 thread)
+    orc.lib().orc_set_threads(1)
+    orc.mathconst(x, 2.0, 1)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        orc.mathconst(x, 2.0, 1)
+    dt = (time.perf_counter() - t0) / iters
+    res["cpu_clMultiplyConst_1thread"] = {"us_per_call": dt * 1e6, "Msamples_s": n / dt / 1e6}
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -372,6 +403,7 @@ def main():
         del x, y
         torch.cuda.empty_cache()
         extra = secondary_blocks(torch, blocks, capi, local, sp, hbm_peak)
+        extra["per_call_8192_pageable"] = per_call(blocks, capi, local)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -47,6 +47,8 @@ SIGNATURES = {
     "clb200_select_device": (_i, [_i, _i, _i, _i]),
     "clb200_destroy": (_i, [_vp]),
     "clb200_get_counters": (_i, [_vp, _pu64, _pu64, _pu64]),
+    "clb200_register_host_buffer": (_i, [_vp, C.c_size_t]),
+    "clb200_unregister_host_buffer": (_i, [_vp]),
     "clb200_mathconst_create": (_i, [_i, _i, _f, _i, _ph]),
     "clb200_mathconst_set_k": (_i, [_vp, _f]),
     "clb200_mathconst_k": (_f, [_vp]),

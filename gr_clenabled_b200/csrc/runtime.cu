@@ -30,6 +30,17 @@ int device_sm_count(int device)
     return cache[device];
 }
 
+size_t small_call_bytes()
+{
+    static long v = -1;
+    if (v < 0) {
+        const char *e = getenv("CLB200_SMALL_KB");
+        long kb = e ? atol(e) : 1024;
+        v = (kb >= 0 && kb <= (1 << 20) ? kb : 1024) << 10;
+    }
+    return (size_t)v;
+}
+
 size_t chunk_target_bytes()
 {
     static size_t v = 0;
@@ -162,6 +173,20 @@ int clb200_select_device(int platform_type, int dev_selector, int platform_id, i
     int dev = (dev_selector == 2) ? dev_id : 0;   // OCLDEVICESELECTOR_SPECIFIC=2 (GRCLBase.h:69-70)
     CLB_CHECK(dev >= 0 && dev < n, CLB200_EINVAL, "device %d requested, %d present", dev, n);
     return dev;
+}
+
+int clb200_register_host_buffer(void *ptr, size_t bytes)
+{
+    CLB_CHECK(ptr != nullptr && bytes > 0, CLB200_EINVAL, "bad host range");
+    CLB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return CLB200_OK;
+}
+
+int clb200_unregister_host_buffer(void *ptr)
+{
+    CLB_CHECK(ptr != nullptr, CLB200_EINVAL, "null pointer");
+    CLB_CUDA(cudaHostUnregister(ptr));
+    return CLB200_OK;
 }
 
 int clb200_destroy(clb200_handle h)

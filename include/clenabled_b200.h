@@ -27,6 +27,7 @@
 #ifndef CLENABLED_B200_H
 #define CLENABLED_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -86,6 +87,12 @@ CLB200_API int clb200_select_device(int platform_type, int dev_selector, int pla
 CLB200_API int clb200_destroy(clb200_handle h);           /* any handle; GRCLBase::cleanup/stop */
 /* counters since creation: bytes H2D, bytes D2H, kernel launches */
 CLB200_API int clb200_get_counters(clb200_handle h, uint64_t *h2d, uint64_t *d2h, uint64_t *launches);
+
+/* Optional: page-lock a caller-owned host range (e.g. a GNU Radio circular buffer,
+ * once, in start()) so that work() calls on it skip the staging copy and are DMA'd /
+ * read by the kernels in place.  The range must stay valid until unregistered.   */
+CLB200_API int clb200_register_host_buffer(void *ptr, size_t bytes);
+CLB200_API int clb200_unregister_host_buffer(void *ptr);
 
 /* ------------------------------------------------------------ clMathConst -- */
 /* clMathConst::make(idataType,..,fValue,operatorType,..) include/clenabled/clMathConst.h:51
