@@ -174,12 +174,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_xengine_tc(XeParams p)
         qok[i] = s < p.A;
     }
 
-    auto load_stage = [&](int sg, uint32_t (&pre)[QPT][4]) {
-        const int grp = sg / nst, st = sg - grp * nst;
-        const int f0 = grp * FC;
+    // Stages are loaded strictly in sequence, so a cursor (group, stage, base pointer)
+    // replaces per-stage divisions and 64-bit address rebuilds.
+    int ld_grp = s0 / nst, ld_st = s0 - ld_grp * nst;
+    auto load_stage = [&](int, uint32_t (&pre)[QPT][4]) {
+        const int f0 = ld_grp * FC, st = ld_st;
         const int8_t *sbase = p.in + ((long)(p.f_off + f0)) * NPOL * 2 + (long)st * XE_TT * frameb;
         const int trem = p.T - st * XE_TT;
         const bool full = p.aligned && (f0 + FC <= p.F) && (p.A == ASTN);
+        if (++ld_st == nst) {
+            ld_st = 0;
+            ld_grp++;
+        }
         if (full && trem >= XE_TT) {
             const unsigned fb = (unsigned)frameb;
 #pragma unroll
