@@ -289,10 +289,61 @@ class clXEngine_impl : public clXEngine
     std::vector<char> d_buf;                  // one integration, [t][station][chan][pol]
     std::vector<gr_complex> d_matrix;
     int d_tracker = 0, d_pipeline_count = 0;
+    // file sink (lib/clXEngine_impl.cc:393-465, :1259-1277): raw cf32_le frames + JSON sidecar
+    bool d_output_file;
+    std::string d_file_base, d_object_name, d_filename;
+    std::vector<std::string> d_antennas;
+    long d_rollover_bytes, d_bytes_written = 0, d_sync_timestamp, d_frames = 0;
+    int d_rollover_index = 0, d_first_channel;
+    double d_chan_freq, d_chan_width;
+    FILE *d_fp = nullptr;
+
+    bool open_file()
+    {
+        if (d_fp) fclose(d_fp);
+        d_filename = d_file_base;
+        if (d_rollover_bytes > 0) {                         // "_NNN" suffix (:405-412)
+            char suffix[16];
+            snprintf(suffix, sizeof(suffix), "_%03d", d_rollover_index++);
+            d_filename += suffix;
+        }
+        d_fp = fopen(d_filename.c_str(), "wb");
+        d_bytes_written = 0;
+        if (!d_fp) return false;
+        // sidecar with the reference's keys (:438-465)
+        FILE *js = fopen((d_filename + ".json").c_str(), "w");
+        if (js) {
+            std::string names = "[";
+            for (size_t i = 0; i < d_antennas.size(); i++) names += (i ? ",\"" : "\"") + d_antennas[i] + "\"";
+            names += "]";
+            const long ntime = (long)d_integration * (d_pipeline > 1 ? d_pipeline : 1);
+            fprintf(js,
+                    "{\n\"sync_timestamp\":%ld,\n\"first_seq_num\":%ld,\n\"object_name\":\"%s\",\n"
+                    "\"num_baselines\":%d,\n\"first_channel\":%d,\n\"first_channel_center_freq\":%f,\n"
+                    "\"channels\":%d,\n\"channel_width\":%f,\n\"polarizations\":%d,\n\"antennas\":%d,\n"
+                    "\"antenna_names\":%s,\n\"ntime\":%ld,\n\"samples_per_block\":%ld,\n"
+                    "\"bytes_per_block\":%ld,\n\"data_type\":\"cf32_le\",\n\"data_format\": \"triangular order\"\n}\n",
+                    d_sync_timestamp, d_frames * ntime, d_object_name.c_str(), d_num_inputs * (d_num_inputs + 1) / 2,
+                    d_first_channel, d_chan_freq, d_num_channels, d_chan_width, d_npol, d_num_inputs, names.c_str(),
+                    ntime, (long)d_matrix.size(), (long)(d_matrix.size() * sizeof(gr_complex)));
+            fclose(js);
+        }
+        return true;
+    }
+    void write_frame()
+    {
+        const long bytes = (long)(d_matrix.size() * sizeof(gr_complex));
+        if (!d_fp || (d_rollover_bytes > 0 && d_bytes_written + bytes > d_rollover_bytes))
+            if (!open_file()) return;
+        d_bytes_written += (long)fwrite(d_matrix.data(), 1, bytes, d_fp);
+        d_frames++;
+    }
 
 public:
     clXEngine_impl(int dev, int data_type, int polarization, int num_inputs, int num_channels, int integration,
-                   bool disable_output, int pipeline_integration)
+                   bool disable_output, int pipeline_integration, bool output_file, const std::string &file_base,
+                   int rollover_size_mb, const std::vector<std::string> &antenna_list, long sync_timestamp,
+                   const std::string &object_name, int first_channel, double chan_freq, double chan_width)
         : gr::block("clXEngine",
                     gr::io_signature::make(2, num_inputs * (data_type == DTYPE_PACKEDXY ? 1 : polarization),
                                            num_channels * (data_type == DTYPE_PACKEDXY ? 2
@@ -300,7 +351,10 @@ public:
                                                                                        : (int)sizeof(gr_complex))),
                     gr::io_signature::make(0, 0, 0)),
           d_data_type(data_type), d_npol(polarization), d_num_inputs(num_inputs), d_num_channels(num_channels),
-          d_integration(integration), d_pipeline(pipeline_integration), d_disable_output(disable_output)
+          d_integration(integration), d_pipeline(pipeline_integration), d_disable_output(disable_output),
+          d_output_file(output_file), d_file_base(file_base), d_object_name(object_name), d_antennas(antenna_list),
+          d_rollover_bytes((long)rollover_size_mb * 1000000L), d_sync_timestamp(sync_timestamp),
+          d_first_channel(first_channel), d_chan_freq(chan_freq), d_chan_width(chan_width)
     {
         must(clb200_xengine_create(dev, data_type, polarization, num_inputs, num_channels, integration, &d.h),
              num_inputs < 2);                   // std::out_of_range, clXEngine_impl.cc:106-109
@@ -309,6 +363,18 @@ public:
         d_matrix.resize((size_t)clb200_xengine_output_items(d.h));
         message_port_register_out(pmt::mp("xcorr"));                 // :294-295
         message_port_register_out(pmt::mp("sync"));
+    }
+    ~clXEngine_impl() override
+    {
+        if (d_fp) fclose(d_fp);
+    }
+    bool stop() override
+    {
+        if (d_fp) {
+            fclose(d_fp);
+            d_fp = nullptr;
+        }
+        return true;
     }
     void forecast(int noutput_items, gr_vector_int &req) override
     {
@@ -348,7 +414,8 @@ public:
             d_pipeline_count++;
             if (d_pipeline < 2 || d_pipeline_count >= d_pipeline) {
                 d_pipeline_count = 0;
-                if (!d_disable_output)
+                if (d_output_file) write_frame();                    // :1259-1277
+                else if (!d_disable_output)
                     message_port_pub(pmt::mp("xcorr"),
                                      pmt::cons(pmt::string_to_symbol("triang_matrix"),
                                                pmt::init_c32vector(d_matrix.size(), d_matrix.data())));   // :1076-1080
@@ -418,13 +485,16 @@ clPolyphaseChannelizer::sptr clPolyphaseChannelizer::make(int plat, int sel, int
                                                                       num_channels, ninputs_per_iter, ch_map));
 }
 clXEngine::sptr clXEngine::make(int plat, int sel, int pid, int did, bool, int data_type, int polarization,
-                                int num_inputs, int, int, int num_channels, int integration,
-                                std::vector<std::string>, bool, std::string, int, bool, long, std::string, double,
-                                double, bool disable_output, int pipeline_integration)
+                                int num_inputs, int, int first_channel, int num_channels, int integration,
+                                std::vector<std::string> antenna_list, bool output_file, std::string file_base,
+                                int rollover_size_mb, bool, long sync_timestamp, std::string object_name,
+                                double starting_chan_center_freq, double channel_width, bool disable_output,
+                                int pipeline_integration)
 {
-    return gnuradio::get_initial_sptr(new clXEngine_impl(pick_device(plat, sel, pid, did), data_type, polarization,
-                                                         num_inputs, num_channels, integration, disable_output,
-                                                         pipeline_integration));
+    return gnuradio::get_initial_sptr(new clXEngine_impl(
+        pick_device(plat, sel, pid, did), data_type, polarization, num_inputs, num_channels, integration,
+        disable_output, pipeline_integration, output_file, file_base, rollover_size_mb, antenna_list, sync_timestamp,
+        object_name, first_channel, starting_chan_center_freq, channel_width));
 }
 
 } // namespace clenabled

@@ -153,6 +153,33 @@ int main()
             CHECK(m[0].imag() == 0.0f);
         }
         CHECK(throws<std::out_of_range>([&] { clXEngine::make(GPU, FIRST, 0, 0, false, DTYPE_BYTE, 1, 1, 1, 0, F, T, {}); }));
+        // file sink: raw cf32_le frames + JSON sidecar (lib/clXEngine_impl.cc:393-465)
+        const char *base = "/tmp/clb200_xengine_test.bin";
+        auto fblk = clXEngine::make(GPU, FIRST, 0, 0, false, DTYPE_BYTE, npol, A, 1, 0, F, T, {"a1", "a2", "a3", "a4"},
+                                    true, base, 0, false, 1234, "obj", 1.0e9, 250e3);
+        CHECK(fblk->general_work(T, ni, iv, ov) == T);
+        CHECK(fblk->general_work(T, ni, iv, ov) == T);
+        fblk->stop();
+        FILE *fp = fopen(base, "rb");
+        CHECK(fp != nullptr);
+        if (fp) {
+            fseek(fp, 0, SEEK_END);
+            CHECK(ftell(fp) == 2L * F * (A * (A + 1) / 2) * npol * npol * (long)sizeof(gr_complex));
+            fclose(fp);
+        }
+        FILE *js = fopen("/tmp/clb200_xengine_test.bin.json", "r");
+        CHECK(js != nullptr);
+        if (js) {
+            char buf[2048];
+            size_t n = fread(buf, 1, sizeof(buf) - 1, js);
+            buf[n] = 0;
+            fclose(js);
+            std::string t(buf);
+            CHECK(t.find("\"sync_timestamp\":1234") != std::string::npos);
+            CHECK(t.find("\"num_baselines\":10") != std::string::npos);
+            CHECK(t.find("\"antenna_names\":[\"a1\",\"a2\",\"a3\",\"a4\"]") != std::string::npos);
+            CHECK(t.find("\"data_type\":\"cf32_le\"") != std::string::npos);
+        }
     }
     if (failures == 0) printf("ALL OK\n");
     return failures == 0 ? 0 : 1;
