@@ -57,6 +57,7 @@ struct XeParams {
     int l2_rows;            // prefetch whole (t, station) rows into L2 ahead of the demand loads
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
+    int dbg;                // timing experiments only (CLB200_XE_DBG): 1 no MMA, 2 no transpose, 4 no epilogue
 };
 
 // which row tiles warp share Q of WPC owns
@@ -357,6 +358,7 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 
 } // namespace
 #include "xengine_tc.cuh"
+#include "xengine_tma.cuh"
 namespace {
 
 // packed 4-bit (hi nibble re, lo nibble im) -> int8 pairs; LUT of CharToComplex (:833)
@@ -449,7 +451,10 @@ struct XEngine : clb200_block {
     int Ftotal = 0, f_first = 0;       // channel shard within the caller's buffer
     const XeVariant *var = nullptr;
     bool use_tc = false;
-    Buf d_in[2], d_unpacked, d_acc, d_out;
+    bool use_tma = false;              // TMA-fed variant of the tcgen05 kernel (needs 16 B aligned rows)
+    int l2promo = 0;
+    int fc_override = 0;               // CLB200_XE_FC: channels per CTA of the TMA kernel (8 | 16)
+    Buf d_in[2], d_unpacked, d_acc, d_out, d_part, d_count;
     Buf pin_in[2], pin_out;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
@@ -472,6 +477,8 @@ struct XEngine : clb200_block {
         }
         d_unpacked.release();
         d_acc.release();
+        d_part.release();
+        d_count.release();
         d_out.release();
         pin_out.release();
         if (ev_done) cudaEventDestroy(ev_done);
@@ -509,10 +516,21 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     }
     const XeVariant *v = x->var;
     const bool tc = x->use_tc;                         // tcgen05/TMEM kernel (<= 32 rows of inputs)
-    const int fc = tc ? TC_FC : v->fc;
+    const long nout = x->out_items();
+    long rowb = (long)Fstride * x->npol * 2;
+    const bool tma_ok = tc && x->use_tma && ((uintptr_t)src % 16 == 0) && (rowb % 16 == 0) &&
+                        ((uintptr_t)out_i32 % 8 == 0) && ((uintptr_t)out_f32 % 8 == 0);
+    // TMA kernel: 8 channels per CTA while 16 would leave SMs without a channel group (then no CTA
+    // has to share a group with another one: no time slicing, no cross-CTA reduction)
+    int fc = tc ? TC_FC : v->fc;
+    if (tma_ok) {
+        fc = ((x->F + 15) / 16 < sms) ? 8 : 16;
+        if (x->fc_override == 8 || x->fc_override == 16) fc = x->fc_override;
+    }
+    const int kt = tma_ok ? 512 / fc : XE_TT;           // time steps per stage
     const int ngroups = (x->F + fc - 1) / fc;
     // fewer channel groups than ~2 waves of CTAs: split the integrations over time as well
-    const int nst = (T + XE_TT - 1) / XE_TT;
+    const int nst = (T + kt - 1) / kt;
     // few channel groups: one wave of (slice, group) CTAs; many: whole groups per CTA
     int tslices = 0;
     if (ngroups < sms && nst > 1) tslices = std::min(nst, std::max(1, sms / ngroups));
@@ -524,8 +542,24 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     const int nslice = split ? 2 : 1;
     const int grid = tslices > 0 ? ngroups * tslices
                                  : (int)std::min<long>(sms, split ? (long)ngroups * nst : ngroups);
-    const long nout = x->out_items();
-    if (nslice > 1) {
+    CUtensorMap tmap;
+    const bool tma = tma_ok && tm_make_map(&tmap, src, rowb, x->A, T, x->npol, fc, x->l2promo);
+    CLB_CHECK(tma || !tma_ok, CLB200_ECUDA, "clXEngine: cuTensorMapEncodeTiled failed");
+    // TMA kernel, time-sliced: the slices of a channel group meet in a partial-sum workspace and the
+    // last CTA to arrive writes the final visibilities -- no memset, no atomics, no conversion pass
+    const bool fixup = tma && tslices > 1;
+    TmFix fx{nullptr, nullptr, nullptr};
+    if (fixup) {
+        CLB_TRY(x->d_part.reserve((size_t)tslices * nout * 8));
+        const size_t cb = (size_t)ngroups * sizeof(unsigned) + 64 * sizeof(long long);
+        if (x->d_count.cap < cb) {
+            CLB_TRY(x->d_count.reserve(cb));
+            CLB_CUDA(cudaMemsetAsync(x->d_count.p, 0, x->d_count.cap, st));   // counters return to zero by themselves
+        }
+        fx.part = (int2 *)x->d_part.p;
+        fx.count = (unsigned *)x->d_count.p;
+        fx.stamp = (long long *)((char *)x->d_count.p + ((size_t)ngroups * sizeof(unsigned) + 7) / 8 * 8);
+    } else if (nslice > 1) {
         // partial sums meet in an int32 buffer through atomics
         if (out_i32 == nullptr) {
             CLB_TRY(x->d_acc.reserve((size_t)nout * 8));
@@ -536,7 +570,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     }
     XeParams p;
     p.in = src;
-    p.out_i32 = (nslice > 1 && out_i32 == nullptr) ? (int32_t *)x->d_acc.p : out_i32;
+    p.out_i32 = (!fixup && nslice > 1 && out_i32 == nullptr) ? (int32_t *)x->d_acc.p : out_i32;
     p.out_f32 = out_f32;
     p.split = split ? 1 : 0;
     p.nslice = tslices;
@@ -551,10 +585,15 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.f_off = f_off;
     p.T = T;
     p.accumulate = accumulate;
+    {
+        const char *e = getenv("CLB200_XE_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     p.scale = scale;
-    long rowb = (long)Fstride * x->npol * 2;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
-    if (tc) {
+    if (tma) {
+        tm_kernel(x->npol, fc)<<<grid, TM_THREADS, TM_SMEM, st>>>(p, fx, tmap);
+    } else if (tc) {
         if (x->npol == 1) k_xengine_tc<1><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
         else k_xengine_tc<2><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
     } else {
@@ -562,7 +601,14 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     }
     CLB_CUDA(cudaGetLastError());
     x->n_launch++;
-    if (nslice > 1 && out_f32 != nullptr) {
+    if ((p.dbg & 8) && fx.stamp) {
+        long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, fx.stamp, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "xe stamps (cycles): loop %lld  tmem->stage %lld  publish %lld  final %lld\n", h[0] - h[4],
+                h[1] - h[0], h[2] - h[1], h[3] - h[2]);
+    }
+    if (!fixup && nslice > 1 && out_f32 != nullptr) {
         k_i32_to_f32<<<grid_for((nout + 255) / 256, sms, 8), 256, 0, st>>>(
             (const int2 *)p.out_i32, out_f32, nout, scale, accumulate);
         CLB_CUDA(cudaGetLastError());
@@ -708,6 +754,19 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
                           : cudaFuncSetAttribute((const void *)k_xengine_tc<2>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        const char *notma = getenv("CLB200_XE_TMA");           // 0: keep the LDG-fed tcgen05 kernel
+        if (x->use_tc && e == cudaSuccess && !(notma && atoi(notma) == 0)) {
+            cudaError_t e2 = cudaFuncSetAttribute((const void *)tm_kernel(npol, 8),
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM);
+            if (e2 == cudaSuccess)
+                e2 = cudaFuncSetAttribute((const void *)tm_kernel(npol, 16),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM);
+            x->use_tma = (e2 == cudaSuccess) && tm_encoder() != nullptr;
+            const char *fo = getenv("CLB200_XE_FC");
+            x->fc_override = fo ? atoi(fo) : 0;
+            const char *pr = getenv("CLB200_XE_L2PROMO");
+            x->l2promo = pr ? atoi(pr) : 0;
+        }
     }
     if (e != cudaSuccess) {
         set_error("clXEngine: cannot reserve %d B of shared memory: %s", x->var->smem_bytes,

@@ -280,6 +280,25 @@ def test_xengine_ichar_bit_exact(A, F, T, npol):
     assert rel_err(vis, orc.xengine_f32(buf, A, F, T, npol)) < TOL
 
 
+@pytest.mark.parametrize("A,F,T,npol", [(32, 64, 256, 1), (8, 16, 64, 1), (16, 32, 128, 2)])
+def test_xengine_ldg_feed_kernel_bit_exact(A, F, T, npol, monkeypatch):
+    """The LDG-fed tcgen05 kernel stays the fallback for rows that are not 16 B aligned; force it."""
+    monkeypatch.setenv("CLB200_XE_TMA", "0")
+    buf = orc.rng_i8(T * A * F * npol * 2, orc.SEED_X + 9)
+    got = _xe(capi.DTYPE_BYTE, npol, A, F, T).work_i32(buf)
+    assert np.array_equal(got, orc.xengine_exact(buf, A, F, T, npol))
+
+
+@pytest.mark.parametrize("A,F,T,npol", [(32, 48, 1000, 1), (30, 40, 77, 1), (16, 24, 200, 2), (13, 8, 31, 2)])
+def test_xengine_tma_feed_ragged_bit_exact(A, F, T, npol):
+    """TMA-fed kernel (16 B aligned rows): channel counts that are not a multiple of the 16-channel
+    group, station counts below the box, time steps that do not fill the last 32-step stage --
+    the out-of-range part of every box is zero-filled by the TMA unit."""
+    buf = orc.rng_i8(T * A * F * npol * 2, orc.SEED_X + 10)
+    got = _xe(capi.DTYPE_BYTE, npol, A, F, T).work_i32(buf)
+    assert np.array_equal(got, orc.xengine_exact(buf, A, F, T, npol))
+
+
 def test_xengine_extreme_values_do_not_overflow():
     A, F, T = 32, 4, 1024
     buf = np.full(T * A * F * 2, -128, np.int8)               # worst case |sum| = 2*128*128*1024 < 2^31
