@@ -454,7 +454,8 @@ struct XEngine : clb200_block {
     bool use_tma = false;              // TMA-fed variant of the tcgen05 kernel (needs 16 B aligned rows)
     int l2promo = 0;
     int fc_override = 0;               // CLB200_XE_FC: channels per CTA of the TMA kernel (8 | 16)
-    Buf d_in[2], d_unpacked, d_acc, d_out, d_part, d_count;
+    bool pdl = true;                   // programmatic dependent launch (CLB200_XE_PDL=0 turns it off)
+    Buf d_in[2], d_unpacked, d_acc, d_out, d_count;
     Buf pin_in[2], pin_out;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
@@ -477,7 +478,6 @@ struct XEngine : clb200_block {
         }
         d_unpacked.release();
         d_acc.release();
-        d_part.release();
         d_count.release();
         d_out.release();
         pin_out.release();
@@ -524,7 +524,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     // has to share a group with another one: no time slicing, no cross-CTA reduction)
     int fc = tc ? TC_FC : v->fc;
     if (tma_ok) {
-        fc = ((x->F + 15) / 16 < sms) ? 8 : 16;
+        fc = ((x->F + 15) / 16 * 8 < sms) ? 8 : 16;      // 16 unless even 8 time slices per group leave SMs idle
         if (x->fc_override == 8 || x->fc_override == 16) fc = x->fc_override;
     }
     const int kt = tma_ok ? 512 / fc : XE_TT;           // time steps per stage
@@ -538,6 +538,12 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         const char *e = getenv("CLB200_XE_SLICES");       // tuning override: 0 = stream-K split
         if (e && ngroups < 2 * sms && nst > 1) tslices = std::min(nst, atoi(e));
     }
+    if (tma_ok && tslices > 1) {
+        // the slices of a group are the CTAs of one cluster: 2, 4 or 8, each finalising fc/slices channels
+        int c = 2;
+        while (c * 2 <= std::min(tslices, std::min(8, fc))) c *= 2;
+        tslices = c;
+    }
     const bool split = (tslices > 1) || (tslices == 0 && ngroups < 2 * sms && nst > 1);
     const int nslice = split ? 2 : 1;
     const int grid = tslices > 0 ? ngroups * tslices
@@ -545,21 +551,15 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     CUtensorMap tmap;
     const bool tma = tma_ok && tm_make_map(&tmap, src, rowb, x->A, T, x->npol, fc, x->l2promo);
     CLB_CHECK(tma || !tma_ok, CLB200_ECUDA, "clXEngine: cuTensorMapEncodeTiled failed");
-    // TMA kernel, time-sliced: the slices of a channel group meet in a partial-sum workspace and the
-    // last CTA to arrive writes the final visibilities -- no memset, no atomics, no conversion pass
+    // TMA kernel, time-sliced: the slices of a channel group form a thread-block cluster and meet
+    // through distributed shared memory -- no memset, no atomics, no conversion pass
     const bool fixup = tma && tslices > 1;
-    TmFix fx{nullptr, nullptr, nullptr};
-    if (fixup) {
-        CLB_TRY(x->d_part.reserve((size_t)tslices * nout * 8));
-        const size_t cb = (size_t)ngroups * sizeof(unsigned) + 64 * sizeof(long long);
-        if (x->d_count.cap < cb) {
-            CLB_TRY(x->d_count.reserve(cb));
-            CLB_CUDA(cudaMemsetAsync(x->d_count.p, 0, x->d_count.cap, st));   // counters return to zero by themselves
-        }
-        fx.part = (int2 *)x->d_part.p;
-        fx.count = (unsigned *)x->d_count.p;
-        fx.stamp = (long long *)((char *)x->d_count.p + ((size_t)ngroups * sizeof(unsigned) + 7) / 8 * 8);
-    } else if (nslice > 1) {
+    TmFix fx{nullptr};
+    if (tma && getenv("CLB200_XE_DBG")) {
+        CLB_TRY(x->d_count.reserve(64 * sizeof(long long)));
+        fx.stamp = (long long *)x->d_count.p;
+    }
+    if (!fixup && nslice > 1) {
         // partial sums meet in an int32 buffer through atomics
         if (out_i32 == nullptr) {
             CLB_TRY(x->d_acc.reserve((size_t)nout * 8));
@@ -592,7 +592,21 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.scale = scale;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
     if (tma) {
-        tm_kernel(x->npol, fc)<<<grid, TM_THREADS, TM_SMEM, st>>>(p, fx, tmap);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TM_THREADS);
+        cfg.dynamicSmemBytes = TM_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = fixup ? tslices : 1;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = x->pdl ? 2 : 1;
+        CLB_CUDA(cudaLaunchKernelEx(&cfg, tm_kernel(x->npol, fc), p, fx, tmap));
     } else if (tc) {
         if (x->npol == 1) k_xengine_tc<1><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
         else k_xengine_tc<2><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
@@ -602,11 +616,14 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     CLB_CUDA(cudaGetLastError());
     x->n_launch++;
     if ((p.dbg & 8) && fx.stamp) {
-        long long h[8];
+        long long h[24];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, fx.stamp, sizeof h, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "xe stamps (cycles): loop %lld  tmem->stage %lld  publish %lld  final %lld\n", h[0] - h[4],
-                h[1] - h[0], h[2] - h[1], h[3] - h[2]);
+        for (int c = 0; c < 2; c++)
+            fprintf(stderr, "xe cta %d (ns from cta0 loop start): loop end %lld | staged %lld | B0 %lld | sent %lld | B1 %lld | written %lld | again %lld\n",
+                    c, h[8 * c + 0] - h[7], h[8 * c + 1] - h[7], h[8 * c + 2] - h[7], h[8 * c + 3] - h[7],
+                    h[8 * c + 4] - h[7], h[8 * c + 5] - h[7], h[8 * c + 6] - h[7]);
+        fprintf(stderr, "   write_out cycles: own loads %lld | recv %lld | stores %lld | total %lld\n", h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[16]);
     }
     if (!fixup && nslice > 1 && out_f32 != nullptr) {
         k_i32_to_f32<<<grid_for((nout + 255) / 256, sms, 8), 256, 0, st>>>(
@@ -764,6 +781,8 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
             x->use_tma = (e2 == cudaSuccess) && tm_encoder() != nullptr;
             const char *fo = getenv("CLB200_XE_FC");
             x->fc_override = fo ? atoi(fo) : 0;
+            const char *pd = getenv("CLB200_XE_PDL");
+            x->pdl = !(pd && atoi(pd) == 0);
             const char *pr = getenv("CLB200_XE_L2PROMO");
             x->l2promo = pr ? atoi(pr) : 0;
         }

@@ -59,17 +59,132 @@ __device__ __forceinline__ void tm_stsm(uint32_t addr, const uint32_t (&r)[4])
 // the 16 transpose/epilogue warps only (the MMA and TMA warps never join)
 __device__ __forceinline__ void tm_worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// Extra launch state of the TMA kernel: where partial sums of time-sliced CTAs meet.
+// Extra launch state of the TMA kernel.
 struct TmFix {
-    int2 *part;             // [nslice][F][nbl*npol^2] partial visibilities (re, im) of each time slice
-    unsigned *count;        // [groups] arrival counters, zero between launches (the last CTA resets them)
     long long *stamp;       // debug time stamps (or null)
 };
 
-// phase time stamps of CTA 0 (CLB200_XE_DBG & 8): fx.stamp[k] = clock64 at phase k
-#define TM_STAMP(k)                                                                                  \
-    do {                                                                                             \
-        if ((p.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0 && fx.stamp) fx.stamp[k] = clock64(); \
+__device__ __forceinline__ uint32_t tm_mapa(uint32_t saddr, int rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tm_mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tm_mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "TMW_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra TMD_%=;\n\t"
+        "bra TMW_%=;\n\t"
+        "TMD_%=:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Final visibilities of `nch` channels starting at channel f0: staged partial sums (`stg`, channel
+// stride spp) plus `nrecv` received blocks of the same shape, written in output order
+// [channel][baseline][pol^2] as int32 pairs and/or scaled floats (= or +=).
+template <int NPOL>
+__device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg, const int2 *recv, int nrecv,
+                                             int rstride, int spp, int npp, int f0, int nch, int tid, long long *dbgc = nullptr)
+{
+    if (dbgc && tid == 0) dbgc[0] = clock64();
+    int2 *const oi = reinterpret_cast<int2 *>(p.out_i32) + (long)f0 * npp;
+    float2 *const of = p.out_f32 + (long)f0 * npp;
+    const bool has_i = p.out_i32 != nullptr, has_f = p.out_f32 != nullptr;
+    const bool rmw = p.accumulate != 0, redo = p.split && p.nslice <= 1;
+    const float scale = p.scale;
+    const int nit = nch * npp, pad = spp - npp;
+    // item i = (channel, visibility r): the staging stride per channel is spp, the output's is npp.
+    // The epilogue runs once per CTA with only 4 warps per scheduler, so it is bound by the LENGTH of
+    // its dependent chains: batches of UN items, every load of a batch issued before the first use.
+    constexpr int UN = 5;
+    int r = tid, si = tid;
+    while (r >= npp) {
+        r -= npp;
+        si += pad;
+    }
+    for (int i0 = tid; i0 < nit; i0 += UN * XE_THREADS) {
+        int sk[UN];
+        int2 v[UN];
+#pragma unroll
+        for (int k = 0; k < UN; k++) {
+            sk[k] = si;
+            r += XE_THREADS;
+            si += XE_THREADS;
+            while (r >= npp) {
+                r -= npp;
+                si += pad;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UN; k++) v[k] = (i0 + k * XE_THREADS < nit) ? stg[sk[k]] : make_int2(0, 0);
+        if (dbgc && tid == 0 && i0 == 0) dbgc[1] = clock64() + (v[0].x & 0);
+#pragma unroll 1
+        for (int s = 0; s < nrecv; s++) {
+            int2 w[UN];
+#pragma unroll
+            for (int k = 0; k < UN; k++)
+                w[k] = (i0 + k * XE_THREADS < nit) ? recv[s * rstride + sk[k]] : make_int2(0, 0);
+#pragma unroll
+            for (int k = 0; k < UN; k++) {
+                v[k].x += w[k].x;
+                v[k].y += w[k].y;
+            }
+        }
+        if (dbgc && tid == 0 && i0 == 0) dbgc[2] = clock64() + (v[0].x & 0);
+        if (redo || rmw) {                               // rare paths
+#pragma unroll
+            for (int k = 0; k < UN; k++) {
+                const int i = i0 + k * XE_THREADS;
+                if (i < nit) {
+                    if (redo) {                          // stream-K: partial groups meet in memory
+                        atomicAdd(&oi[i].x, v[k].x);
+                        atomicAdd(&oi[i].y, v[k].y);
+                    } else {
+                        if (has_i) {
+                            const int2 q = oi[i];
+                            oi[i] = make_int2(v[k].x + q.x, v[k].y + q.y);
+                        }
+                        if (has_f) {
+                            const float2 q = of[i];
+                            of[i] = make_float2((float)v[k].x * scale + q.x, (float)v[k].y * scale + q.y);
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        if (has_i) {
+#pragma unroll
+            for (int k = 0; k < UN; k++)
+                if (i0 + k * XE_THREADS < nit) oi[i0 + k * XE_THREADS] = v[k];
+        }
+        if (has_f) {
+#pragma unroll
+            for (int k = 0; k < UN; k++)
+                if (i0 + k * XE_THREADS < nit)
+                    of[i0 + k * XE_THREADS] = make_float2((float)v[k].x * scale, (float)v[k].y * scale);
+        }
+        if (dbgc && tid == 0 && i0 == 0) dbgc[3] = clock64();
+    }
+    if (dbgc && tid == 0) dbgc[4] = clock64();
+}
+
+// phase time stamps of CTAs 0 and 1 (CLB200_XE_DBG & 8): fx.stamp[8 * cta + k] = globaltimer (ns) at phase k
+#define TM_STAMP(k)                                                                         \
+    do {                                                                                    \
+        if ((p.dbg & 8) && blockIdx.x < 2 && threadIdx.x == 0 && fx.stamp) {                \
+            unsigned long long t_;                                                          \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                          \
+            fx.stamp[8 * blockIdx.x + (k)] = (long long)t_;                                 \
+        }                                                                                   \
     } while (0)
 
 // FC = channels per CTA: 16 fills the 512 TMEM columns; 8 (256 columns) lets 1024 channels spread over
@@ -102,24 +217,29 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
     uint64_t *rfull = bars + 2 * TM_NI;              // [NR]  raw box landed
     uint64_t *rempty = bars + 2 * TM_NI + TM_NR;     // [NR]  raw box transposed
     uint64_t *tfree = bars + 2 * TM_NI + 2 * TM_NR;  //       epilogue drained TMEM
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfree + 1);
-    unsigned *last_flag = tmem_slot + 1;
+    uint64_t *pdone = tfree + 1;                     //       every peer of the cluster is past its main loop
+    uint64_t *pdata = tfree + 2;                     //       every peer's partial sums have arrived
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfree + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int CS = (p.dbg & 16) ? KS * 2048 : CSK;            // experiment: unskewed (128 B aligned) images
     const int nbl = p.A * (p.A + 1) / 2;
     const int npp = nbl * NPOL * NPOL;                       // visibilities per channel
-    const int spp = npp + 4;                                 // staging stride per channel (int2): breaks the bank tie
+    const int spp = (npp + 5) & ~1;                          // staging stride per channel (int2): breaks the bank tie, even -> 16 B blocks
     const int ngroups = (p.F + FC - 1) / FC;
     const int nst = (p.T + KT - 1) / KT;
 
-    int s0, s1, slice = 0;
+    // Time-sliced launches (nslice > 1) are CLUSTER launches: the nslice CTAs of a cluster share one
+    // channel group, each integrates a slice of the time steps, and the partial visibilities meet
+    // through distributed shared memory (no atomics, no workspace, no second kernel).
+    const bool clustered = p.nslice > 1;
+    int s0, s1, slice = 0, grp_c = 0;
     if (p.nslice > 0) {
-        const int grp = blockIdx.x % ngroups;
-        slice = blockIdx.x / ngroups;
+        grp_c = clustered ? blockIdx.x / p.nslice : blockIdx.x;
+        slice = clustered ? blockIdx.x % p.nslice : 0;
         const int len = (nst + p.nslice - 1) / p.nslice;
-        s0 = grp * nst + slice * len;
-        s1 = min(grp * nst + nst, s0 + len);
+        s0 = grp_c * nst + slice * len;
+        s1 = min(grp_c * nst + nst, s0 + len);
     } else if (p.split) {
         const long total = (long)ngroups * nst;
         s0 = (int)(total * blockIdx.x / gridDim.x);
@@ -130,8 +250,11 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
     }
     // a time slice may be empty (more slices than stages); it still takes part in the slice fix-up
     const int nstages = max(0, s1 - s0);
-    if (nstages == 0 && !(p.nslice > 1)) return;
+    if (nstages == 0 && !clustered) return;
 
+    // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as SMs free up;
+    // it runs its own prologue and then waits (griddepcontrol.wait below) for this grid to complete.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
             (uint32_t)__cvta_generic_to_shared(tmem_slot)), "n"(FC * 32));
@@ -147,11 +270,17 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
             tc_mbar_init(&rempty[r], XE_WARPS);
         }
         tc_mbar_init(tfree, XE_WARPS);
+        tc_mbar_init(pdone, max(p.nslice - 1, 1));
+        tc_mbar_init(pdata, max(p.nslice - 1, 1) * XE_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // everything above overlapped the previous grid's tail; from here on global memory is touched
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // peers signal each other's mbarriers: those must be initialised cluster-wide before anyone proceeds
+    if (clustered) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == XE_WARPS + 1) {
@@ -169,6 +298,14 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
                     grp++;
                 }
             }
+        }
+        __syncwarp();
+        if (clustered) {
+            // the raw ring is idle once the last boxes are transposed: tell the peers they may send
+            for (int n = max(0, nstages - TM_NR); n < nstages; n++)
+                tc_mbar_wait(&rempty[n % TM_NR], (uint32_t)(n / TM_NR) & 1u);
+            if (lane < p.nslice && lane != slice)
+                tm_mbar_arrive_remote(tm_mapa((uint32_t)__cvta_generic_to_shared(pdone), lane));
         }
     } else if (warp == XE_WARPS) {
         // ---- MMA issue: the warp stays converged, one ELECTED lane issues (a plain `lane == 0` branch
@@ -228,7 +365,7 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
             }
         }
         const int tid = threadIdx.x;                               // 0..511 (worker warps come first)
-        TM_STAMP(4);
+        TM_STAMP(7);
         for (int n = 0; n < max(nstages, 1); n++) {
             const int sg = s0 + n, b = n % TM_NI, r = n % TM_NR;
             if (nstages > 0) {
@@ -264,7 +401,7 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
             // there in OUTPUT order [channel][baseline][pol^2](re, im) and leave as ONE contiguous block
             // (the output is channel-major, lib/clXEngine_impl.cc:799-806).
             TM_STAMP(0);
-            const int grp_e = (p.nslice > 0) ? (int)(blockIdx.x % ngroups) : sg / nst;
+            const int grp_e = (p.nslice > 0) ? grp_c : sg / nst;
             const int f0 = grp_e * FC;
             if (nstages > 0) {
                 const int wq = warp & 3;
@@ -280,6 +417,7 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
                     else ob = chl * spp + 4 * (st1 * (st1 + 1) / 2) + 2 * (v1 & 1);
 #pragma unroll 1
                     for (int half = 0; half < 2; half++) {
+                        if (half == 1 && wq < 2) break;                // columns 16..31 only pair with rows >= 16
                         uint32_t rg[32];
                         tc_ld32(tmem_base + (((uint32_t)wq * 32u) << 16) +
                                     (uint32_t)(((warp >> 2) + 4 * jj) * 64 + half * 32), rg);
@@ -299,105 +437,59 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(tfree);
             }
-            tm_worker_sync();
             TM_STAMP(1);
-            const int nch = min(FC, p.F - f0);
-            const int nit = nch * npp;                                 // int2 items of this block
-            const long gbase = (long)f0 * npp;
-            const bool fix = p.nslice > 1;
-            bool last = true;
-            constexpr int UN = 4;
-            if (fix) {
-                // every slice publishes its partial block; the last one to arrive folds the others in
-                if (nstages > 0) {
-                    int2 *dst = fx.part + (long)slice * p.F * npp + gbase;
-                    for (int i = tid; i < nit; i += XE_THREADS) {
-                        const int ch = i / npp;
-                        dst[i] = stg[i + ch * (spp - npp)];
-                    }
-                }
-                __threadfence();
-                tm_worker_sync();
-                if (tid == 0) *last_flag = atomicAdd(&fx.count[grp_e], 1u);
-                tm_worker_sync();
-                last = (*last_flag == (unsigned)(p.nslice - 1));
-                if (last) __threadfence();
-            }
-            TM_STAMP(2);
-            if (last) {
-                const int len = (nst + p.nslice - 1) / max(p.nslice, 1);
-                for (int i0 = tid; i0 < nit; i0 += UN * XE_THREADS) {
-                    int2 v[UN];
-                    int2 oi[UN];
-                    float2 of[UN];
-#pragma unroll
-                    for (int k = 0; k < UN; k++) {
-                        const int i = i0 + k * XE_THREADS;
-                        v[k] = make_int2(0, 0);
-                        if (i < nit && nstages > 0) v[k] = stg[i + (i / npp) * (spp - npp)];
-                    }
-                    if (fix)
-                        for (int s = 0; s < p.nslice; s++) {
-                            if (s == slice || s * len >= nst) continue;         // own or empty slice
-                            const int2 *src = fx.part + (long)s * p.F * npp + gbase;
-                            int2 w[UN];
-#pragma unroll
-                            for (int k = 0; k < UN; k++) {
-                                const int i = i0 + k * XE_THREADS;
-                                w[k] = (i < nit) ? __ldcg(src + i) : make_int2(0, 0);
-                            }
-#pragma unroll
-                            for (int k = 0; k < UN; k++) {
-                                v[k].x += w[k].x;
-                                v[k].y += w[k].y;
-                            }
-                        }
-                    if (p.split && !fix) {                         // stream-K: partial groups meet in memory
-#pragma unroll
-                        for (int k = 0; k < UN; k++) {
-                            const int i = i0 + k * XE_THREADS;
-                            if (i < nit) {
-                                atomicAdd(p.out_i32 + 2 * (gbase + i), v[k].x);
-                                atomicAdd(p.out_i32 + 2 * (gbase + i) + 1, v[k].y);
-                            }
-                        }
-                        continue;
-                    }
-                    if (p.accumulate) {
-#pragma unroll
-                        for (int k = 0; k < UN; k++) {
-                            const int i = i0 + k * XE_THREADS;
-                            if (i < nit && p.out_i32) oi[k] = reinterpret_cast<int2 *>(p.out_i32)[gbase + i];
-                            if (i < nit && p.out_f32) of[k] = p.out_f32[gbase + i];
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < UN; k++) {
-                        const int i = i0 + k * XE_THREADS;
-                        if (i >= nit) continue;
-                        if (p.out_i32) {
-                            int2 o = v[k];
-                            if (p.accumulate) {
-                                o.x += oi[k].x;
-                                o.y += oi[k].y;
-                            }
-                            reinterpret_cast<int2 *>(p.out_i32)[gbase + i] = o;
-                        }
-                        if (p.out_f32) {
-                            float2 o = make_float2((float)v[k].x * p.scale, (float)v[k].y * p.scale);
-                            if (p.accumulate) {
-                                o.x += of[k].x;
-                                o.y += of[k].y;
-                            }
-                            p.out_f32[gbase + i] = o;
-                        }
-                    }
-                }
-                if (fix && tid == 0) fx.count[grp_e] = 0;
-            }
+            if (clustered) break;                                      // the exchange below needs every thread
             tm_worker_sync();
-            TM_STAMP(3);
+            tm_write_out<NPOL>(p, stg, nullptr, 0, 0, spp, npp, f0, min(FC, p.F - f0), tid);
+            tm_worker_sync();
+            TM_STAMP(5);
         }
+    }
+    if (clustered && warp < XE_WARPS) {
+        // ---- cluster exchange: rank r finalises channels [r*nc, (r+1)*nc) of the group.  A rank's raw ring
+        // is idle once its last box is transposed (its TMA lane tells the peers through their `pdone`
+        // mbarriers); it then receives the peers' staged partial sums of its channels (16 B remote stores),
+        // each sending warp signalling the receiver's `pdata`.  One-way signals instead of cluster-wide
+        // barriers (~1 us each here).  Measured slower: one cp.async.bulk shared::cta -> shared::cluster
+        // copy per peer (34 KiB took ~1.3 us to land). ----
+        const int CL = p.nslice, nc = FC / CL, blk = nc * spp;         // int2 items per (rank, peer) block
+        const int tid = threadIdx.x;
+        tm_worker_sync();                                              // staging complete
+        tm_mbar_wait_cluster(pdone, 0);
+        TM_STAMP(2);
+        for (int q = 0; q < CL; q++) {
+            if (q == slice) continue;
+            const int slot = slice < q ? slice : slice - 1;
+            const uint32_t remote = tm_mapa(raw_addr + (uint32_t)(slot * blk * 8), q);
+            const int4 *src = reinterpret_cast<const int4 *>(stg + q * blk);
+            constexpr int UN = 5;
+            for (int i0 = tid; i0 < blk / 2; i0 += UN * XE_THREADS) {
+                int4 v[UN];
+#pragma unroll
+                for (int k = 0; k < UN; k++)
+                    v[k] = (i0 + k * XE_THREADS < blk / 2 && nstages > 0) ? src[i0 + k * XE_THREADS] : make_int4(0, 0, 0, 0);
+#pragma unroll
+                for (int k = 0; k < UN; k++)
+                    if (i0 + k * XE_THREADS < blk / 2)
+                        asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                         remote + (uint32_t)(i0 + k * XE_THREADS) * 16u),
+                                     "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w)
+                                     : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) tm_mbar_arrive_remote(tm_mapa((uint32_t)__cvta_generic_to_shared(pdata), q));
+        }
+        TM_STAMP(3);
+        const int f0 = grp_c * FC + slice * nc;
+        if (nstages == 0) {
+            for (int i = tid; i < blk; i += XE_THREADS) stg[slice * blk + i] = make_int2(0, 0);
+            tm_worker_sync();
+        }
+        tm_mbar_wait_cluster(pdata, 0);
+        TM_STAMP(4);
+        tm_write_out<NPOL>(p, stg + slice * blk, reinterpret_cast<const int2 *>(sptr), CL - 1, blk, spp, npp, f0,
+                           min(nc, p.F - f0), tid, ((p.dbg & 8) && blockIdx.x == 0) ? fx.stamp + 16 : nullptr);
+        TM_STAMP(5);
     }
     tc_fence_before();
     __syncthreads();

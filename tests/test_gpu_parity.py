@@ -289,11 +289,15 @@ def test_xengine_ldg_feed_kernel_bit_exact(A, F, T, npol, monkeypatch):
     assert np.array_equal(got, orc.xengine_exact(buf, A, F, T, npol))
 
 
-@pytest.mark.parametrize("A,F,T,npol", [(32, 48, 1000, 1), (30, 40, 77, 1), (16, 24, 200, 2), (13, 8, 31, 2)])
+@pytest.mark.parametrize("A,F,T,npol", [(32, 48, 1000, 1), (30, 40, 77, 1), (16, 24, 200, 2), (13, 8, 31, 2),
+                                         (32, 256, 512, 1), (32, 64, 512, 1), (16, 16, 300, 2), (32, 128, 96, 1),
+                                         (32, 2400, 64, 1), (5, 8, 2048, 1)])
 def test_xengine_tma_feed_ragged_bit_exact(A, F, T, npol):
-    """TMA-fed kernel (16 B aligned rows): channel counts that are not a multiple of the 16-channel
-    group, station counts below the box, time steps that do not fill the last 32-step stage --
-    the out-of-range part of every box is zero-filled by the TMA unit."""
+    """TMA-fed kernel (16 B aligned rows): channel counts that are not a multiple of the channel
+    group, station counts below the box, time steps that do not fill the last stage (the out-of-range
+    part of every box is zero-filled by the TMA unit); few channel groups -> clusters of 2, 4 and 8
+    time-slice CTAs exchanging partial sums through distributed shared memory; many groups -> 16
+    channels per CTA, several groups per CTA."""
     buf = orc.rng_i8(T * A * F * npol * 2, orc.SEED_X + 10)
     got = _xe(capi.DTYPE_BYTE, npol, A, F, T).work_i32(buf)
     assert np.array_equal(got, orc.xengine_exact(buf, A, F, T, npol))

@@ -20,9 +20,11 @@ def run(tag, **env):
     for i in range(16): blk.launch_device_i32(bufs[i % 4].data_ptr(), acc.data_ptr(), sp)
     e1.record(); torch.cuda.synchronize()
     print("%-40s %7.1f us" % (tag, e0.elapsed_time(e1) / 16 * 1e3), flush=True)
-for fc, sl in ((16, 2), (8, 1)):
-    kw = dict(FC=fc, SLICES=sl)
-    run("fc=%d no epilogue, skewed" % fc, DBG=4, **kw)
-    run("fc=%d no epilogue, aligned images" % fc, DBG=4 + 16, **kw)
-    run("fc=%d no epi, no transpose, skewed" % fc, DBG=6, **kw)
-    run("fc=%d no epi, no transpose, aligned" % fc, DBG=6 + 16, **kw)
+run("fc=16 sl=2 full", FC=16, SLICES=2)
+run("fc=16 sl=2 no epilogue", FC=16, SLICES=2, DBG=4)
+run("fc=8 full", FC=8)
+run("default", )
+os.environ["CLB200_XE_DBG"] = "8"; os.environ["CLB200_XE_SLICES"] = "2"; os.environ["CLB200_XE_FC"] = "16"
+blk = blocks.clXEngine(1, 1, 0, 0, False, capi.DTYPE_BYTE, 1, A, 1, 0, F, T, [])
+for i in range(3): blk.launch_device_i32(bufs[i % 4].data_ptr(), acc.data_ptr(), sp)
+torch.cuda.synchronize()

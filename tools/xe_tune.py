@@ -19,7 +19,7 @@ ref = None
 
 def run(tag, **env):
     global ref
-    for k in ("CLB200_XE_TMA", "CLB200_XE_SLICES", "CLB200_XE_L2PROMO", "CLB200_XE_LEGACY", "CLB200_XE_FC"):
+    for k in ("CLB200_XE_TMA", "CLB200_XE_SLICES", "CLB200_XE_L2PROMO", "CLB200_XE_LEGACY", "CLB200_XE_FC", "CLB200_XE_PDL"):
         os.environ.pop(k, None)
     for k, v in env.items():
         os.environ["CLB200_XE_" + k] = str(v)
@@ -44,8 +44,9 @@ def run(tag, **env):
 
 run("ldg feed (r1 kernel)", TMA=0)
 run("tma default")
-for fc in (8, 16):
-    for sl in (1, 2):
-        run("tma fc=%d slices=%d" % (fc, sl), FC=fc, SLICES=sl)
-run("tma fc=8 l2promo=2", FC=8, L2PROMO=2)
-run("tma fc=8 l2promo=3", FC=8, L2PROMO=3)
+run("tma default, no PDL", PDL=0)
+run("tma fc=8", FC=8)
+run("tma fc=8, no PDL", FC=8, PDL=0)
+run("tma fc=16 slices=2", FC=16, SLICES=2)
+run("tma fc=16 slices=2, no PDL", FC=16, SLICES=2, PDL=0)
+run("tma default (again)")
