@@ -68,53 +68,78 @@ def ncu_traffic(nvec):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  The default run's timed region is a
+    few milliseconds, far below nvidia-smi's own start-up time, so the samples come from NVML directly
+    (nvidia_ml_py, ~1 ms period, a thread in this process); the sampler starts before the last warm-up
+    steps so that it also sees the clocks under load just before the region.  `sm_mhz` is the median of
+    the samples taken inside the timed region when there are any (else of the under-load ones)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.thr = index, [], None, None
+        self.index, self.rows, self.thr, self.run = index, [], None, False
+        self.t0 = self.t1 = None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES renumbers CUDA ordinals, NVML does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
         except Exception:
-            self.proc = None
+            self.nv = None
             return
+        self.run = True
+
         def rd():
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+            nv = self.nv
+            while self.run:
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((time.perf_counter(), sm, rs))
+                except Exception:
+                    pass
+                time.sleep(0.001)
         self.thr = threading.Thread(target=rd, daemon=True)
         self.thr.start()
 
+    def mark(self, which):
+        if which == 0:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
+
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.run = False
+        self.thr.join(timeout=1)
         try:
-            self.proc.wait(timeout=2)
+            mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            mx = None
+        inside = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        use = inside if inside else self.rows
+        sm = sorted(r[1] for r in use)
+        bits = 0
+        for r in use:
+            bits |= r[2]
+        reasons = sorted(nm for b, nm in self.REASONS.items() if bits & b)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(self.rows),
+                "samples_in_timed_region": len(inside), "reasons": reasons,
+                "how": "NVML, 1 ms period, started 3 warm-up steps before the timed region"}
 
 
 # --------------------------------------------------------------------------------
@@ -307,20 +332,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
     l0 = fft.counters()["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark(0)
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
+    sampler.mark(1)
     ms = e0.elapsed_time(e1)
     launches = fft.counters()["launches"] - l0
     clocks = sampler.stop() if rank == 0 else None

@@ -57,7 +57,6 @@ struct XeParams {
     int l2_rows;            // prefetch whole (t, station) rows into L2 ahead of the demand loads
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
-    int dbg;                // timing experiments only (CLB200_XE_DBG): 1 no MMA, 2 no transpose, 4 no epilogue
 };
 
 // which row tiles warp share Q of WPC owns
@@ -455,7 +454,7 @@ struct XEngine : clb200_block {
     int l2promo = 0;
     int fc_override = 0;               // CLB200_XE_FC: channels per CTA of the TMA kernel (8 | 16)
     bool pdl = true;                   // programmatic dependent launch (CLB200_XE_PDL=0 turns it off)
-    Buf d_in[2], d_unpacked, d_acc, d_out, d_count;
+    Buf d_in[2], d_unpacked, d_acc, d_out;
     Buf pin_in[2], pin_out;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
@@ -478,7 +477,6 @@ struct XEngine : clb200_block {
         }
         d_unpacked.release();
         d_acc.release();
-        d_count.release();
         d_out.release();
         pin_out.release();
         if (ev_done) cudaEventDestroy(ev_done);
@@ -554,11 +552,6 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     // TMA kernel, time-sliced: the slices of a channel group form a thread-block cluster and meet
     // through distributed shared memory -- no memset, no atomics, no conversion pass
     const bool fixup = tma && tslices > 1;
-    TmFix fx{nullptr};
-    if (tma && getenv("CLB200_XE_DBG")) {
-        CLB_TRY(x->d_count.reserve(64 * sizeof(long long)));
-        fx.stamp = (long long *)x->d_count.p;
-    }
     if (!fixup && nslice > 1) {
         // partial sums meet in an int32 buffer through atomics
         if (out_i32 == nullptr) {
@@ -585,10 +578,6 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.f_off = f_off;
     p.T = T;
     p.accumulate = accumulate;
-    {
-        const char *e = getenv("CLB200_XE_DBG");
-        p.dbg = e ? atoi(e) : 0;
-    }
     p.scale = scale;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
     if (tma) {
@@ -606,7 +595,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = x->pdl ? 2 : 1;
-        CLB_CUDA(cudaLaunchKernelEx(&cfg, tm_kernel(x->npol, fc), p, fx, tmap));
+        CLB_CUDA(cudaLaunchKernelEx(&cfg, tm_kernel(x->npol, fc), p, tmap));
     } else if (tc) {
         if (x->npol == 1) k_xengine_tc<1><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
         else k_xengine_tc<2><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
@@ -615,16 +604,6 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     }
     CLB_CUDA(cudaGetLastError());
     x->n_launch++;
-    if ((p.dbg & 8) && fx.stamp) {
-        long long h[24];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, fx.stamp, sizeof h, cudaMemcpyDeviceToHost);
-        for (int c = 0; c < 2; c++)
-            fprintf(stderr, "xe cta %d (ns from cta0 loop start): loop end %lld | staged %lld | B0 %lld | sent %lld | B1 %lld | written %lld | again %lld\n",
-                    c, h[8 * c + 0] - h[7], h[8 * c + 1] - h[7], h[8 * c + 2] - h[7], h[8 * c + 3] - h[7],
-                    h[8 * c + 4] - h[7], h[8 * c + 5] - h[7], h[8 * c + 6] - h[7]);
-        fprintf(stderr, "   write_out cycles: own loads %lld | recv %lld | stores %lld | total %lld\n", h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[16]);
-    }
     if (!fixup && nslice > 1 && out_f32 != nullptr) {
         k_i32_to_f32<<<grid_for((nout + 255) / 256, sms, 8), 256, 0, st>>>(
             (const int2 *)p.out_i32, out_f32, nout, scale, accumulate);

@@ -59,11 +59,6 @@ __device__ __forceinline__ void tm_stsm(uint32_t addr, const uint32_t (&r)[4])
 // the 16 transpose/epilogue warps only (the MMA and TMA warps never join)
 __device__ __forceinline__ void tm_worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// Extra launch state of the TMA kernel.
-struct TmFix {
-    long long *stamp;       // debug time stamps (or null)
-};
-
 __device__ __forceinline__ uint32_t tm_mapa(uint32_t saddr, int rank)
 {
     uint32_t r;
@@ -92,9 +87,8 @@ __device__ __forceinline__ void tm_mbar_wait_cluster(uint64_t *bar, uint32_t par
 // [channel][baseline][pol^2] as int32 pairs and/or scaled floats (= or +=).
 template <int NPOL>
 __device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg, const int2 *recv, int nrecv,
-                                             int rstride, int spp, int npp, int f0, int nch, int tid, long long *dbgc = nullptr)
+                                             int rstride, int spp, int npp, int f0, int nch, int tid)
 {
-    if (dbgc && tid == 0) dbgc[0] = clock64();
     int2 *const oi = reinterpret_cast<int2 *>(p.out_i32) + (long)f0 * npp;
     float2 *const of = p.out_f32 + (long)f0 * npp;
     const bool has_i = p.out_i32 != nullptr, has_f = p.out_f32 != nullptr;
@@ -125,7 +119,6 @@ __device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg,
         }
 #pragma unroll
         for (int k = 0; k < UN; k++) v[k] = (i0 + k * XE_THREADS < nit) ? stg[sk[k]] : make_int2(0, 0);
-        if (dbgc && tid == 0 && i0 == 0) dbgc[1] = clock64() + (v[0].x & 0);
 #pragma unroll 1
         for (int s = 0; s < nrecv; s++) {
             int2 w[UN];
@@ -138,7 +131,6 @@ __device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg,
                 v[k].y += w[k].y;
             }
         }
-        if (dbgc && tid == 0 && i0 == 0) dbgc[2] = clock64() + (v[0].x & 0);
         if (redo || rmw) {                               // rare paths
 #pragma unroll
             for (int k = 0; k < UN; k++) {
@@ -172,27 +164,15 @@ __device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg,
                 if (i0 + k * XE_THREADS < nit)
                     of[i0 + k * XE_THREADS] = make_float2((float)v[k].x * scale, (float)v[k].y * scale);
         }
-        if (dbgc && tid == 0 && i0 == 0) dbgc[3] = clock64();
     }
-    if (dbgc && tid == 0) dbgc[4] = clock64();
 }
-
-// phase time stamps of CTAs 0 and 1 (CLB200_XE_DBG & 8): fx.stamp[8 * cta + k] = globaltimer (ns) at phase k
-#define TM_STAMP(k)                                                                         \
-    do {                                                                                    \
-        if ((p.dbg & 8) && blockIdx.x < 2 && threadIdx.x == 0 && fx.stamp) {                \
-            unsigned long long t_;                                                          \
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                          \
-            fx.stamp[8 * blockIdx.x + (k)] = (long long)t_;                                 \
-        }                                                                                   \
-    } while (0)
 
 // FC = channels per CTA: 16 fills the 512 TMEM columns; 8 (256 columns) lets 1024 channels spread over
 // 128 CTAs WITHOUT slicing time, i.e. without any cross-CTA reduction.  A raw box is always 32 KiB:
 // KT = 512 / FC time steps (KS = KT / 32 MMA k-steps per stage).
 template <int NPOL, int FC>
 __global__ void __launch_bounds__(TM_THREADS, 1)
-k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
+k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int IB = FC * NPOL * 2;                        // bytes per (t, station) run: 16 | 32 | 64
     constexpr int NH = IB / 16;                              // 16 B chunks per run
@@ -222,7 +202,7 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfree + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int CS = (p.dbg & 16) ? KS * 2048 : CSK;            // experiment: unskewed (128 B aligned) images
+    constexpr int CS = CSK;
     const int nbl = p.A * (p.A + 1) / 2;
     const int npp = nbl * NPOL * NPOL;                       // visibilities per channel
     const int spp = (npp + 5) & ~1;                          // staging stride per channel (int2): breaks the bank tie, even -> 16 B blocks
@@ -320,7 +300,6 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
             if (group_first && n > 0) tc_mbar_wait(tfree, (uint32_t)(groups_done - 1) & 1u);
             tc_fence_after();
             if (leader) {
-                if (!(p.dbg & 1))
 #pragma unroll
                     for (int ks = 0; ks < KS; ks++)
 #pragma unroll
@@ -365,14 +344,13 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
             }
         }
         const int tid = threadIdx.x;                               // 0..511 (worker warps come first)
-        TM_STAMP(7);
         for (int n = 0; n < max(nstages, 1); n++) {
             const int sg = s0 + n, b = n % TM_NI, r = n % TM_NR;
             if (nstages > 0) {
                 tc_mbar_wait(&rfull[r], (uint32_t)(n / TM_NR) & 1u);
                 if (n >= TM_NI) tc_mbar_wait(&empty[b], (uint32_t)(n / TM_NI - 1) & 1u);   // MMAs of stage n-NI are done
                 const uint32_t src = raw_addr + r * TM_RAWB, dst = img_addr + b * TM_IMGB;
-                if (!(p.dbg & 2)) {
+                {
                     uint32_t v[UPW][4];
 #pragma unroll
                     for (int i = 0; i < UPW; i++) tm_ldsm_t8(src + ld_off[i], v[i]);
@@ -390,17 +368,10 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
                 tc_mbar_wait(&empty[b], (uint32_t)(n / TM_NI) & 1u);       // every MMA of the group has landed
                 tc_fence_after();
             }
-            if (p.dbg & 4) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(tfree);
-                continue;
-            }
             // ---- epilogue.  All MMAs of the group are done and no worker is ahead of this point, so the
             // image ring is free: the 16 channels are combined (re/im rows sit in adjacent lanes), staged
             // there in OUTPUT order [channel][baseline][pol^2](re, im) and leave as ONE contiguous block
             // (the output is channel-major, lib/clXEngine_impl.cc:799-806).
-            TM_STAMP(0);
             const int grp_e = (p.nslice > 0) ? grp_c : sg / nst;
             const int f0 = grp_e * FC;
             if (nstages > 0) {
@@ -437,12 +408,10 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(tfree);
             }
-            TM_STAMP(1);
             if (clustered) break;                                      // the exchange below needs every thread
             tm_worker_sync();
             tm_write_out<NPOL>(p, stg, nullptr, 0, 0, spp, npp, f0, min(FC, p.F - f0), tid);
             tm_worker_sync();
-            TM_STAMP(5);
         }
     }
     if (clustered && warp < XE_WARPS) {
@@ -456,7 +425,6 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
         const int tid = threadIdx.x;
         tm_worker_sync();                                              // staging complete
         tm_mbar_wait_cluster(pdone, 0);
-        TM_STAMP(2);
         for (int q = 0; q < CL; q++) {
             if (q == slice) continue;
             const int slot = slice < q ? slice : slice - 1;
@@ -479,17 +447,14 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
             __syncwarp();
             if (lane == 0) tm_mbar_arrive_remote(tm_mapa((uint32_t)__cvta_generic_to_shared(pdata), q));
         }
-        TM_STAMP(3);
         const int f0 = grp_c * FC + slice * nc;
         if (nstages == 0) {
             for (int i = tid; i < blk; i += XE_THREADS) stg[slice * blk + i] = make_int2(0, 0);
             tm_worker_sync();
         }
         tm_mbar_wait_cluster(pdata, 0);
-        TM_STAMP(4);
         tm_write_out<NPOL>(p, stg + slice * blk, reinterpret_cast<const int2 *>(sptr), CL - 1, blk, spp, npp, f0,
-                           min(nc, p.F - f0), tid, ((p.dbg & 8) && blockIdx.x == 0) ? fx.stamp + 16 : nullptr);
-        TM_STAMP(5);
+                           min(nc, p.F - f0), tid);
     }
     tc_fence_before();
     __syncthreads();
@@ -498,7 +463,7 @@ k_xengine_tma(XeParams p, TmFix fx, const __grid_constant__ CUtensorMap tmap)
     }
 }
 
-typedef void (*tm_kernel_t)(XeParams, TmFix, const CUtensorMap);
+typedef void (*tm_kernel_t)(XeParams, const CUtensorMap);
 inline tm_kernel_t tm_kernel(int npol, int fc)
 {
     if (npol == 1) return fc == 8 ? &k_xengine_tma<1, 8> : &k_xengine_tma<1, 16>;

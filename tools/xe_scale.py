@@ -23,8 +23,7 @@ def run(tag, T, **env):
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 16 * 1e3
     print("%-34s T=%5d %7.1f us  %6.0f GB/s" % (tag, T, us, T * A * F * 2 / us / 1e3), flush=True)
-for tag, env in (("fc=16 sl=2 TMA only", dict(FC=16, SLICES=2, DBG=7)), ("fc=16 sl=2 full", dict(FC=16, SLICES=2)),
-                 ("fc=8 TMA only", dict(FC=8, DBG=7)), ("fc=8 full", dict(FC=8)), ("fc=8 no epilogue", dict(FC=8, DBG=4)),
-                 ("ldg", dict(TMA=0))):
+for tag, env in (("default (16 ch/CTA, clusters of 2 slices)", dict()), ("8 ch/CTA, no slicing", dict(FC=8)),
+                 ("no programmatic dependent launch", dict(PDL=0)), ("ldg-fed kernel (r1)", dict(TMA=0))):
     for T in (256, 512, 1024, 2048, 4096):
         run(tag, T, **env)
