@@ -362,3 +362,146 @@ class clXEngine(_Block):
 
     def launch_device_i32(self, d_in, d_out, stream=0):
         check(self._lib.clb200_xengine_launch_device_i32(self._h, d_in, d_out, stream))
+
+
+# ------------------------------------------------------------------------------------------
+# SURVEY 8(f) "next" rows
+# ------------------------------------------------------------------------------------------
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+class clXCorrelate(_Block):
+    """clenabled.clXCorrelate (include/clenabled/clXCorrelate.h:56-57).  work() takes the frame of
+    every input and returns what the reference publishes on message port "corr": the dict
+    {"corrvect": float32[n-1], "corrective_lags": int32[n-1]} (lib/clXCorrelate_impl.cc:1585-1593),
+    or None for a frame dropped by decim_frames (:1540-1547)."""
+
+    def __init__(self, openCLPlatformType, devSelector, platformId, devId, setDebug, num_inputs, signal_length,
+                 data_type, data_size, max_search_index, decim_frames, async_=False):
+        super().__init__()
+        if data_size == 0:
+            raise ValueError("Unknown data type.")                               # :710-714
+        self.num_inputs, self.signal_length, self.dtype = int(num_inputs), int(signal_length), int(data_type)
+        self.decim_frames, self._frame = int(decim_frames), 1
+        dev = self._device(openCLPlatformType, devSelector, platformId, devId)
+        check(self._lib.clb200_xcorrelate_create(dev, self.num_inputs, self.signal_length, self.dtype,
+                                                 int(max_search_index), C.byref(self._h)))
+
+    def max_shift(self):
+        return self._lib.clb200_xcorrelate_max_shift(self._h)
+
+    def work(self, inputs):
+        if self.decim_frames > 1:
+            keep = (self._frame % self.decim_frames) == 0
+            self._frame += 1
+            if keep:
+                self._frame = 1
+            else:
+                return None
+        arrs = [_in(x, _NP[self.dtype])[:self.signal_length] for x in inputs]
+        assert len(arrs) == self.num_inputs and all(a.size == self.signal_length for a in arrs)
+        arrs = [np.ascontiguousarray(a) for a in arrs]
+        corr = np.zeros(self.num_inputs - 1, np.float32)
+        lag = np.zeros(self.num_inputs - 1, np.int32)
+        check(self._lib.clb200_xcorrelate_work(self._h, _ptr_array(arrs), _ptr(corr), _ptr(lag)))
+        return {"corrvect": corr, "corrective_lags": lag}
+
+    def factors(self, signal):
+        out = np.zeros(2 * self.max_shift(), np.float32)
+        check(self._lib.clb200_xcorrelate_factors(self._h, signal, _ptr(out), out.size))
+        return out
+
+    def launch_device(self, d_in, d_corr, d_lag, stream=0):
+        check(self._lib.clb200_xcorrelate_launch_device(self._h, d_in, d_corr, d_lag, stream))
+
+
+class clxcorrelate_fft_vcf(_Block):
+    """clenabled.clxcorrelate_fft_vcf (include/clenabled/clxcorrelate_fft_vcf.h:49)."""
+
+    def __init__(self, fftSize, num_inputs, openCLPlatformType, devSelector, platformId, devId, input_type=1):
+        super().__init__()
+        self.n, self.num_inputs = int(fftSize), int(num_inputs)
+        dev = self._device(openCLPlatformType, devSelector, platformId, devId)
+        check(self._lib.clb200_xcorr_fft_create(self.n, self.num_inputs, int(input_type), dev, C.byref(self._h)))
+
+    def work(self, inputs):
+        """inputs: num_inputs arrays of nvec*fftSize complex; returns num_inputs-1 float arrays."""
+        arrs = [_in(x, c64) for x in inputs]
+        nvec = arrs[0].size // self.n
+        outs = [np.zeros(nvec * self.n, np.float32) for _ in range(self.num_inputs - 1)]
+        check(self._lib.clb200_xcorr_fft_work(self._h, _ptr_array(arrs), _ptr_array(outs), nvec))
+        return outs
+
+    def launch_device(self, d_ins, d_outs, nvec, stream=0):
+        a = (C.c_void_p * len(d_ins))(*d_ins)
+        o = (C.c_void_p * len(d_outs))(*d_outs)
+        check(self._lib.clb200_xcorr_fft_launch_device(self._h, a, o, nvec, stream))
+
+
+class clComplexFilter(_Block):
+    """clenabled.clComplexFilter (include/clenabled/clComplexFilter.h:706): complex taps, time domain."""
+
+    def __init__(self, openclPlatform, devSelector, platformId, devId, decimation, taps, nthreads=1, setDebug=0):
+        super().__init__()
+        self.decimation = int(decimation)
+        dev = self._device(openclPlatform, devSelector, platformId, devId)
+        t = np.ascontiguousarray(taps, c64)
+        check(self._lib.clb200_cfilter_create(dev, self.decimation, _ptr(t), t.size, C.byref(self._h)))
+
+    def set_taps2(self, taps):
+        t = np.ascontiguousarray(taps, c64)
+        check(self._lib.clb200_cfilter_set_taps(self._h, _ptr(t), t.size))
+
+    def work(self, x):
+        x = _in(x, c64)
+        out = np.zeros(x.size // self.decimation + 2, c64)
+        n_out = C.c_long(0)
+        check(self._lib.clb200_cfilter_work(self._h, _ptr(x), x.size, _ptr(out), C.byref(n_out)))
+        return out[:n_out.value]
+
+    def launch_device(self, d_in, n_in, d_out, stream=0):
+        n_out = C.c_long(0)
+        check(self._lib.clb200_cfilter_launch_device(self._h, d_in, n_in, d_out, C.byref(n_out), stream))
+        return n_out.value
+
+
+class clQuadratureDemod(_Block):
+    """clenabled.clQuadratureDemod (include/clenabled/clQuadratureDemod.h:49)."""
+
+    def __init__(self, gain, openCLPlatformType, devSelector, platformId, devId, setDebug=0):
+        super().__init__()
+        dev = self._device(openCLPlatformType, devSelector, platformId, devId)
+        check(self._lib.clb200_quaddemod_create(dev, float(gain), C.byref(self._h)))
+
+    def work(self, x):
+        x = _in(x, c64)
+        out = np.zeros(x.size, np.float32)
+        check(self._lib.clb200_quaddemod_work(self._h, _ptr(x), _ptr(out), x.size))
+        return out
+
+    def launch_device(self, d_in, d_out, nitems, stream=0):
+        check(self._lib.clb200_quaddemod_launch_device(self._h, d_in, d_out, nitems, stream))
+
+
+class clSignalSource(_Block):
+    """clenabled.clSignalSource (include/clenabled/clSignalSource.h:49-50)."""
+
+    def __init__(self, idataType, openCLPlatformType, devSelector, platformId, devId, samp_rate, waveform, freq,
+                 amplitude, setDebug=0):
+        super().__init__()
+        self.dtype = int(idataType)
+        dev = self._device(openCLPlatformType, devSelector, platformId, devId)
+        check(self._lib.clb200_sigsource_create(dev, self.dtype, float(samp_rate), int(waveform), float(freq),
+                                                float(amplitude), C.byref(self._h)))
+
+    def phase(self):
+        return self._lib.clb200_sigsource_phase(self._h)
+
+    def work(self, nitems):
+        out = np.zeros(nitems, _NP[self.dtype])
+        check(self._lib.clb200_sigsource_work(self._h, _ptr(out), nitems))
+        return out
+
+    def launch_device(self, d_out, nitems, stream=0):
+        check(self._lib.clb200_sigsource_launch_device(self._h, d_out, nitems, stream))

@@ -89,7 +89,29 @@ SIGNATURES = {
     "clb200_xengine_launch_device": (_i, [_vp, _vp, _vp, _i, _vp]),
     "clb200_xengine_launch_device_i32": (_i, [_vp, _vp, _vp, _vp]),
     "clb200_xengine_set_shard": (_i, [_vp, _i, _i]),
+    "clb200_xcorrelate_create": (_i, [_i, _i, _i, _i, _i, _ph]),
+    "clb200_xcorrelate_max_shift": (_i, [_vp]),
+    "clb200_xcorrelate_work": (_i, [_vp, _ph, _vp, _vp]),
+    "clb200_xcorrelate_launch_device": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "clb200_xcorrelate_factors": (_i, [_vp, _i, _vp, _i]),
+    "clb200_xcorr_fft_create": (_i, [_i, _i, _i, _i, _ph]),
+    "clb200_xcorr_fft_work": (_i, [_vp, _ph, _ph, _l]),
+    "clb200_xcorr_fft_launch_device": (_i, [_vp, _ph, _ph, _l, _vp]),
+    "clb200_cfilter_create": (_i, [_i, _i, _vp, _i, _ph]),
+    "clb200_cfilter_set_taps": (_i, [_vp, _vp, _i]),
+    "clb200_cfilter_work": (_i, [_vp, _vp, _l, _vp, _pl]),
+    "clb200_cfilter_launch_device": (_i, [_vp, _vp, _l, _vp, _pl, _vp]),
+    "clb200_quaddemod_create": (_i, [_i, _f, _ph]),
+    "clb200_quaddemod_work": (_i, [_vp, _vp, _vp, _l]),
+    "clb200_quaddemod_launch_device": (_i, [_vp, _vp, _vp, _l, _vp]),
+    "clb200_sigsource_create": (_i, [_i, _i, C.c_double, _i, C.c_double, C.c_double, _ph]),
+    "clb200_sigsource_work": (_i, [_vp, _vp, _l]),
+    "clb200_sigsource_launch_device": (_i, [_vp, _vp, _l, _vp]),
+    "clb200_sigsource_phase": (C.c_double, [_vp]),
 }
+
+
+SIG_COS, SIG_SIN = 1, 2          # lib/clSignalSource_impl.h:27-28
 
 
 def header_symbols(path=HEADER_PATH):

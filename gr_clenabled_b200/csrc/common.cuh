@@ -47,7 +47,7 @@ void set_error(const char *fmt, ...);
 
 enum BlockKind {
     KIND_MATHCONST = 1, KIND_MATHOP, KIND_UNARY, KIND_SNR, KIND_C2MAGPHASE, KIND_MAGPHASE2C,
-    KIND_FFT, KIND_FILTER, KIND_PFB, KIND_XENGINE
+    KIND_FFT, KIND_FILTER, KIND_PFB, KIND_XENGINE, KIND_XCFFT, KIND_XCORR, KIND_CFILTER, KIND_QUADDEMOD, KIND_SIGSOURCE
 };
 
 int device_sm_count(int device);

@@ -86,6 +86,54 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
     }
 }
 
+// clxcorrelate_fft_vcf (lib/clxcorrelate_fft_vcf_impl.cc:1057-1145) in ONE launch per signal
+// pair instead of the reference's write / MultConj / backward clFFT / ComplexToMag / read /
+// host memcpy-shift per vector: the product ref * conj(sig) (:895-906) is formed while the
+// first pass loads the two spectra, the backward transform (scale 1.0, :727) runs in shared
+// memory, and magnitude (:925-931) + the half swap (:1136-1141) are fused into the last
+// pass' store.  24 B/sample of HBM traffic (2 x 8 in, 4 out... plus 4 B padding-free float out).
+template <int LOGN, int EPT, int BATCH, int MINB>
+__global__ void __launch_bounds__((1 << LOGN) / EPT * BATCH, MINB)
+k_xcfft(const float2 *__restrict__ ref, const float2 *__restrict__ sig, float *__restrict__ out, long nvec,
+        const float2 *__restrict__ tw)
+{
+    using P = Plan<LOGN, EPT>;
+    constexpr int N = P::N, T = P::T;
+    extern __shared__ __align__(16) float2 smem[];
+    const int tb = (BATCH == 1) ? 0 : threadIdx.x / T;
+    const int lt = (BATCH == 1) ? threadIdx.x : threadIdx.x % T;
+    float2 *buf = smem + tb * P::SMEM_F2;
+    const long ntile = (nvec + BATCH - 1) / BATCH;
+    for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long v = tile * BATCH + tb;
+        const bool active = v < nvec;
+        float2 x[EPT];
+        if (active) {
+            const float2 *ra = ref + v * N + lt, *sa = sig + v * N + lt;
+            static_for<0, EPT>([&](auto e_) {
+                constexpr int e = decltype(e_)::value;
+                constexpr int c = in_index<P, EPT>(0, e);
+                const float2 a = ldg_stream(ra + c), b = ldg_stream(sa + c);
+                const float b_i = -b.y;
+                const float re = (a.x * b.x) - (a.y * b_i), im = (a.x * b_i) + (a.y * b.x);
+                x[e] = make_float2(im, re);                  // backward = forward on swapped re/im
+            });
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+        }
+        fft_core<P, EPT>(x, buf, lt, tw);
+        if (active) {
+            float *dst_up = out + v * N + lt + (N >> 1), *dst_dn = out + v * N + lt - (N >> 1);
+            for_each_output_c<P, EPT>(x, [&](auto c_, float2 a) {
+                constexpr int c = decltype(c_)::value;
+                // (re, im) of the backward transform = (a.y, a.x)
+                __stcs(((c & (N >> 1)) ? dst_dn : dst_up) + c, sqrtf(fmaf(a.y, a.y, a.x * a.x)));
+            });
+        }
+    }
+}
+
 // Prefetching variant for the large sizes (one transform per CTA, complex input):
 // the next vector is pulled into the (padded) working buffer by the bulk-copy engine
 // -- one 16*G-byte row per thread, completion on an mbarrier -- as soon as the
@@ -159,6 +207,7 @@ struct FftVariant {
     void (*fill_tw)(std::vector<float2> &);
     void (*kernel[3])(const float2 *, float2 *, long, const float2 *, const float *, int);
     void (*kernel_pf[2])(const float2 *, float2 *, long, const float2 *, const float *, int);   // or null
+    void (*kernel_xc)(const float2 *, const float2 *, float *, long, const float2 *);           // FFT correlator
 };
 
 template <int LOGN, int EPT>
@@ -193,6 +242,7 @@ FftVariant make_variant()
     v.kernel[1] = &k_fft<LOGN, EPT, BATCH, MINB, 1>;     // backward
     v.kernel[2] = &k_fft<LOGN, EPT, BATCH, MINB, 2>;     // forward, real input
     v.kernel_pf[0] = v.kernel_pf[1] = nullptr;
+    v.kernel_xc = &k_xcfft<LOGN, EPT, BATCH, MINB>;
     if constexpr (BATCH == 1 && LOGN >= 12) {
         v.kernel_pf[0] = &k_fft_pf<LOGN, EPT, MINB, 0>;
         v.kernel_pf[1] = &k_fft_pf<LOGN, EPT, MINB, 1>;
@@ -263,9 +313,152 @@ int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st
     return CLB200_OK;
 }
 
+// ------------------------------------------------------------- clxcorrelate_fft_vcf --
+struct XcFft : clb200_block {
+    int n = 0, num_inputs = 0, input_type = 1;
+    const FftVariant *var = nullptr;
+    Buf d_tw, d_spec;              // twiddles; forward spectra of every input (time-series mode)
+    Buf d_in, d_out;               // host-path staging: [num_inputs][nvec][n] c32, [num_inputs-1][nvec][n] f32
+    int resident = 1;
+    cudaStream_t st = nullptr;
+    ~XcFft() override
+    {
+        DeviceGuard g(device);
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        d_tw.release();
+        d_spec.release();
+        d_in.release();
+        d_out.release();
+    }
+};
+
+// d_in[k] : nvec vectors of input k (c32); d_out[k-1] : nvec vectors of float
+int xcfft_launch(XcFft *x, const void *const *d_in, void *const *d_out, long nvec, cudaStream_t st)
+{
+    if (nvec <= 0) return CLB200_OK;
+    const FftVariant *v = x->var;
+    const long ntile = (nvec + v->batch - 1) / v->batch;
+    const int grid = grid_for(ntile, device_sm_count(x->device), x->resident);
+    const float2 *spec[CLB200_XCFFT_MAX_INPUTS];
+    if (x->input_type == 2) {
+        // time series: forward transform of every input first (:1079-1081, :1094-1096)
+        const size_t per = (size_t)nvec * x->n * sizeof(float2);
+        CLB_TRY(x->d_spec.reserve(per * x->num_inputs));
+        for (int k = 0; k < x->num_inputs; k++) {
+            float2 *dst = (float2 *)((char *)x->d_spec.p + per * k);
+            v->kernel[0]<<<grid, v->threads, v->smem_bytes, st>>>((const float2 *)d_in[k], dst, nvec,
+                                                                  (const float2 *)x->d_tw.p, nullptr, 0);
+            x->n_launch++;
+            spec[k] = dst;
+        }
+    } else {
+        for (int k = 0; k < x->num_inputs; k++) spec[k] = (const float2 *)d_in[k];
+    }
+    for (int k = 1; k < x->num_inputs; k++) {
+        v->kernel_xc<<<grid, v->threads, v->smem_bytes, st>>>(spec[0], spec[k], (float *)d_out[k - 1], nvec,
+                                                              (const float2 *)x->d_tw.p);
+        x->n_launch++;
+    }
+    CLB_CUDA(cudaGetLastError());
+    return CLB200_OK;
+}
+
 } // namespace
 
 extern "C" {
+
+int clb200_xcorr_fft_create(int fft_size, int num_inputs, int input_type, int device, clb200_handle *out)
+{
+    CLB_CHECK(out != nullptr, CLB200_EINVAL, "null out");
+    CLB_CHECK(fft_size >= 2 && (fft_size & (fft_size - 1)) == 0 && fft_size <= 16384, CLB200_EINVAL,
+              "clxcorrelate_fft_vcf: fft size %d is not a power of two in 2..16384", fft_size);
+    CLB_CHECK(num_inputs >= 2 && num_inputs <= CLB200_XCFFT_MAX_INPUTS, CLB200_EINVAL,
+              "clxcorrelate_fft_vcf: 2..%d inputs, got %d", CLB200_XCFFT_MAX_INPUTS, num_inputs);
+    CLB_CHECK(input_type == 1 || input_type == 2, CLB200_EINVAL,
+              "clxcorrelate_fft_vcf: input type must be 1 (FFT) or 2 (time series), got %d", input_type);
+    int nd = clb200_device_count();
+    CLB_CHECK(nd > 0, CLB200_ECUDA, "no CUDA device present");
+    CLB_CHECK(device >= 0 && device < nd, CLB200_EINVAL, "device %d out of range", device);
+    DeviceGuard g(device);
+    XcFft *x = new XcFft;
+    x->kind = KIND_XCFFT;
+    x->device = device;
+    x->n = fft_size;
+    x->num_inputs = num_inputs;
+    x->input_type = input_type;
+    x->var = pick_variant(ilog2(fft_size));
+    auto fail = [&](int rc) {
+        delete x;
+        return rc;
+    };
+    std::vector<float2> tw;
+    x->var->fill_tw(tw);
+    if (x->d_tw.reserve(tw.size() * sizeof(float2)) != CLB200_OK) return fail(CLB200_ENOMEM);
+    if (cudaMemcpy(x->d_tw.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("clxcorrelate_fft_vcf: twiddle upload failed");
+        return fail(CLB200_ECUDA);
+    }
+    int occ = 0;
+    cudaError_t e = cudaFuncSetAttribute((const void *)x->var->kernel_xc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         x->var->smem_bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute((const void *)x->var->kernel[0], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 x->var->smem_bytes);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)x->var->kernel_xc, x->var->threads,
+                                                          x->var->smem_bytes);
+    if (e != cudaSuccess || occ < 1) {
+        set_error("clxcorrelate_fft_vcf: kernel for size %d does not fit an SM (%s)", fft_size, cudaGetErrorString(e));
+        return fail(CLB200_ECUDA);
+    }
+    x->resident = occ;
+    *out = x;
+    return CLB200_OK;
+}
+
+int clb200_xcorr_fft_launch_device(clb200_handle h, const void *const *d_in, void *const *d_out, long nvec,
+                                   void *stream)
+{
+    XcFft *x;
+    CLB_TRY(check_kind(h, KIND_XCFFT, &x));
+    CLB_CHECK(d_in && d_out && nvec >= 0, CLB200_EINVAL, "bad arguments");
+    DeviceGuard g(x->device);
+    return xcfft_launch(x, d_in, d_out, nvec, (cudaStream_t)stream);
+}
+
+int clb200_xcorr_fft_work(clb200_handle h, const void *const *in, void *const *out, long nvec)
+{
+    XcFft *x;
+    CLB_TRY(check_kind(h, KIND_XCFFT, &x));
+    CLB_CHECK(in && out && nvec >= 0, CLB200_EINVAL, "bad arguments");
+    if (nvec == 0) return CLB200_OK;
+    DeviceGuard g(x->device);
+    if (!x->st) CLB_CUDA(cudaStreamCreateWithFlags(&x->st, cudaStreamNonBlocking));
+    const size_t ib = (size_t)nvec * x->n * sizeof(float2), ob = (size_t)nvec * x->n * sizeof(float);
+    CLB_TRY(x->d_in.reserve(ib * x->num_inputs));
+    CLB_TRY(x->d_out.reserve(ob * (x->num_inputs - 1)));
+    const void *di[CLB200_XCFFT_MAX_INPUTS];
+    void *dout[CLB200_XCFFT_MAX_INPUTS];
+    for (int k = 0; k < x->num_inputs; k++) {
+        CLB_CHECK(in[k] != nullptr, CLB200_EINVAL, "null input %d", k);
+        di[k] = (char *)x->d_in.p + ib * k;
+        CLB_CUDA(cudaMemcpyAsync((void *)di[k], in[k], ib, cudaMemcpyHostToDevice, x->st));
+        x->n_h2d += ib;
+    }
+    for (int k = 0; k + 1 < x->num_inputs; k++) dout[k] = (char *)x->d_out.p + ob * k;
+    CLB_TRY(xcfft_launch(x, di, dout, nvec, x->st));
+    for (int k = 0; k + 1 < x->num_inputs; k++) {
+        CLB_CHECK(out[k] != nullptr, CLB200_EINVAL, "null output %d", k);
+        CLB_CUDA(cudaMemcpyAsync(out[k], dout[k], ob, cudaMemcpyDeviceToHost, x->st));
+        x->n_d2h += ob;
+    }
+    CLB_CUDA(cudaStreamSynchronize(x->st));
+    return CLB200_OK;
+}
+
 
 int clb200_fft_create(int fft_size, int dir, const float *window, int window_len, int dtype,
                       int device, int shift, clb200_handle *out)

@@ -216,6 +216,81 @@ CLB200_API int clb200_xengine_launch_device_i32(clb200_handle h, const void *d_i
  * total_channels per station; work() gathers only that slab (cudaMemcpy2D).      */
 CLB200_API int clb200_xengine_set_shard(clb200_handle h, int total_channels, int chan_first);
 
+/* ================================================================================
+ * SURVEY 8(f) "next" rows: the blocks either side of the hot path.
+ * ================================================================================ */
+
+/* ---------------------------------------------------------- clXCorrelate -- */
+/* clXCorrelate::make(.., num_inputs, signal_length, data_type, data_size, max_search_index,
+ *   decim_frames, async) include/clenabled/clXCorrelate.h:56-57.  Input 0 is the reference.
+ * Per frame of signal_length samples: magnitude of complex inputs (ComplexToMag,
+ * lib/clXCorrelate_impl.cc:915-929), squares (F32Squared :976-980), one normalised correlation
+ * factor per shift in [-max_shift, max_shift) (XCorrelate :851-900; -2.0 where the overlap has
+ * no energy), then find_max (:1016-1043 + host pass :1371-1413) -> (correlation, corrective lag).
+ * max_shift: max_search_index, or 0.7*signal_length made even, rounded up to a power of two
+ * (:727-747).  signal_length and max_search_index must be even (:715-724).
+ * decim_frames / async are scheduling policies of the block layer above this ABI.          */
+CLB200_API int clb200_xcorrelate_create(int device, int num_inputs, int signal_length, int data_type,
+                                        int max_search_index, clb200_handle *out);
+CLB200_API int clb200_xcorrelate_max_shift(clb200_handle h);
+/* in: num_inputs host pointers to signal_length items each; corr/lag: num_inputs-1 entries
+ * (the "corrvect" / "corrective_lags" vectors of the PDU, :1585-1593)                         */
+CLB200_API int clb200_xcorrelate_work(clb200_handle h, const void *const *in, float *corr, int32_t *lag);
+/* d_in: [num_inputs][signal_length] contiguous device buffer; d_corr/d_lag device outputs   */
+CLB200_API int clb200_xcorrelate_launch_device(clb200_handle h, const void *d_in, float *d_corr,
+                                               int32_t *d_lag, void *stream);
+/* the correlation_factors buffer of the last call for non-reference input `signal` (1-based),
+ * 2*max_shift floats (what the reference's non-kernel find_max path reads back, :1417-1420)  */
+CLB200_API int clb200_xcorrelate_factors(clb200_handle h, int signal, float *out, int cap);
+
+/* ---------------------------------------------------- clxcorrelate_fft_vcf -- */
+/* clxcorrelate_fft_vcf::make(fftSize, num_inputs, .., input_type=1) include/clenabled/
+ *   clxcorrelate_fft_vcf.h:49; input_type 1 = spectra, 2 = time series (forward FFT first).
+ * work (lib/clxcorrelate_fft_vcf_impl.cc:1057-1145): per vector and non-reference input k,
+ *   out[k-1] = fftshift(|IFFT(ref * conj(in[k]))|), backward transform unscaled (:727).         */
+#define CLB200_XCFFT_MAX_INPUTS 32
+CLB200_API int clb200_xcorr_fft_create(int fft_size, int num_inputs, int input_type, int device,
+                                       clb200_handle *out);
+/* in: num_inputs pointers to nvec*fft_size c32; out: num_inputs-1 pointers to nvec*fft_size f32 */
+CLB200_API int clb200_xcorr_fft_work(clb200_handle h, const void *const *in, void *const *out, long nvec);
+CLB200_API int clb200_xcorr_fft_launch_device(clb200_handle h, const void *const *d_in, void *const *d_out,
+                                              long nvec, void *stream);
+
+/* -------------------------------------------------------- clComplexFilter -- */
+/* clComplexFilter::make(.., decimation, const std::vector<gr_complex>& taps, ..)
+ *   include/clenabled/clComplexFilter.h:706; kernel td_FIR_complex_complex
+ *   (lib/clComplexFilter_impl.cc:805-829): out[g] = sum_i taps[K-1-i] * in[g+i] with complex taps.
+ * Streaming semantics as clb200_filter_*: history and decimation phase live in the handle.     */
+CLB200_API int clb200_cfilter_create(int device, int decimation, const float *taps_c32, int ntaps,
+                                     clb200_handle *out);
+CLB200_API int clb200_cfilter_set_taps(clb200_handle h, const float *taps_c32, int ntaps);
+CLB200_API int clb200_cfilter_work(clb200_handle h, const void *in, long n_in, void *out, long *n_out);
+CLB200_API int clb200_cfilter_launch_device(clb200_handle h, const void *d_in, long n_in, void *d_out,
+                                            long *n_out, void *stream);
+
+/* ------------------------------------------------------ clQuadratureDemod -- */
+/* clQuadratureDemod::make(gain, ..) include/clenabled/clQuadratureDemod.h:49; kernel quadDemod
+ *   (lib/clQuadratureDemod_impl.cc:118-143): out[i] = gain * atan2 of x[i+1] * conj(x[i]) in double;
+ *   set_history(2) (:81): the previous call's last sample is kept in the handle (first call: 0).  */
+CLB200_API int clb200_quaddemod_create(int device, float gain, clb200_handle *out);
+CLB200_API int clb200_quaddemod_work(clb200_handle h, const void *in, void *out, long nitems);
+CLB200_API int clb200_quaddemod_launch_device(clb200_handle h, const void *d_in, void *d_out, long nitems,
+                                              void *stream);
+
+/* --------------------------------------------------------- clSignalSource -- */
+/* clSignalSource::make(idataType, .., samp_rate, waveform, freq, amplitude, ..)
+ *   include/clenabled/clSignalSource.h:49-50; kernels sig_float / sig_complex, double branch
+ *   (lib/clSignalSource_impl.cc:128-211): value(index) = f(phase + phase_inc*index) * ampl with
+ *   phase_inc = 2*pi*freq/samp_rate; after each call the phase advances by phase_inc*n and whole
+ *   turns are dropped (:386-398).  waveform: 1 cos, 2 sin (float output); complex = (cos, sin).  */
+#define CLB200_SIG_COS 1   /* SIGSOURCE_COS, lib/clSignalSource_impl.h:27 */
+#define CLB200_SIG_SIN 2
+CLB200_API int clb200_sigsource_create(int device, int data_type, double samp_rate, int waveform,
+                                       double freq, double amplitude, clb200_handle *out);
+CLB200_API int clb200_sigsource_work(clb200_handle h, void *out, long nitems);
+CLB200_API int clb200_sigsource_launch_device(clb200_handle h, void *d_out, long nitems, void *stream);
+CLB200_API double clb200_sigsource_phase(clb200_handle h);
+
 #ifdef __cplusplus
 }
 #endif

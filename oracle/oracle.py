@@ -74,6 +74,19 @@ def lib():
         L.orc_xengine_i8_exact.argtypes = [_bp, _ip, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_xengine_f32.argtypes = [C.c_void_p, C.c_void_p, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_unpack4.argtypes = [_up, _bp, C.c_long]
+        L.orc_xc_mag.argtypes = [_fp, _fp, C.c_long]
+        L.orc_xc_max_shift.argtypes = [C.c_int, C.c_int]
+        L.orc_xc_max_shift.restype = C.c_int
+        L.orc_xc_factors.argtypes = [_fp, _fp, C.c_int, C.c_int, _fp]
+        L.orc_xc_find_max.argtypes = [_fp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.orc_xcorr_fft_vcf.argtypes = [_fp, _fp, _fp, C.c_int, C.c_long, C.c_int]
+        L.orc_xcorr_fft_vcf.restype = C.c_int
+        L.orc_fir_ccc.argtypes = [_fp, _fp, C.c_long, _fp, C.c_int, C.c_int]
+        L.orc_fir_ccc.restype = C.c_long
+        L.orc_quad_demod.argtypes = [_fp, _fp, C.c_long, C.c_float]
+        L.orc_sig_source.argtypes = [_fp, C.c_long, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.orc_sig_source_advance.argtypes = [C.c_double, C.c_double, C.c_long]
+        L.orc_sig_source_advance.restype = C.c_double
         _lib = L
     return _lib
 
@@ -299,3 +312,70 @@ def unpack4(b):
     out = np.zeros(2 * b.size, np.int8)
     lib().orc_unpack4(b, out, b.size)
     return out
+
+
+# ---- SURVEY 8(f) "next" rows ---------------------------------------------------
+XC_GROUP = 1024      # find_max work-group size on a device whose kernel work-group limit is 1024
+
+
+def xc_max_shift(signal_length, max_search_index):
+    return lib().orc_xc_max_shift(signal_length, max_search_index)
+
+
+def xcorrelate(signals, signal_length, max_search_index=0, complex_in=False):
+    """clXCorrelate (lib/clXCorrelate_impl.cc:1528-1594): signals[0] is the reference.
+    Returns (corr float32[n-1], lag int32[n-1], factors float32[n-1][2*max_shift])."""
+    L = signal_length
+    ms = xc_max_shift(L, max_search_index)
+    mags = []
+    for x in signals:
+        if complex_in:
+            x = np.ascontiguousarray(x[:L], np.complex64)
+            m = np.zeros(L, np.float32)
+            lib().orc_xc_mag(_f(x), m, L)
+        else:
+            m = np.ascontiguousarray(x[:L], np.float32)
+        mags.append(m)
+    n = len(signals) - 1
+    corr, lag = np.zeros(n, np.float32), np.zeros(n, np.int32)
+    fac = np.zeros((n, 2 * ms), np.float32)
+    for k in range(n):
+        lib().orc_xc_factors(mags[0], mags[k + 1], L, ms, fac[k])
+        c, i = C.c_float(), C.c_int()
+        lib().orc_xc_find_max(fac[k], 2 * ms, min(2 * ms, XC_GROUP), C.byref(c), C.byref(i))
+        corr[k], lag[k] = c.value, i.value - ms
+    return corr, lag, fac
+
+
+def xcorr_fft_vcf(ref_sig, sig, n, input_type=1):
+    ref_sig = np.ascontiguousarray(ref_sig, np.complex64)
+    sig = np.ascontiguousarray(sig, np.complex64)
+    out = np.zeros(ref_sig.size, np.float32)
+    rc = lib().orc_xcorr_fft_vcf(_f(ref_sig), _f(sig), out, n, ref_sig.size // n, input_type)
+    assert rc == 0
+    return out
+
+
+def fir_ccc(x_with_history, taps, decim=1):
+    x = np.ascontiguousarray(x_with_history, np.complex64)
+    t = np.ascontiguousarray(taps, np.complex64)
+    out = np.zeros(max(0, (x.size - (t.size - 1) + decim - 1) // decim), np.complex64)
+    n = lib().orc_fir_ccc(_f(x), _f(out), x.size, _f(t), t.size, decim)
+    return out[:n]
+
+
+def quad_demod(x_with_history, gain):
+    x = np.ascontiguousarray(x_with_history, np.complex64)
+    out = np.zeros(x.size - 1, np.float32)
+    lib().orc_quad_demod(_f(x), out, out.size, gain)
+    return out
+
+
+def sig_source(n, complex_out, waveform_sin, phase, phase_inc, ampl):
+    out = np.zeros(n, np.complex64 if complex_out else np.float32)
+    lib().orc_sig_source(_f(out), n, int(complex_out), int(waveform_sin), phase, phase_inc, ampl)
+    return out
+
+
+def sig_source_advance(phase, phase_inc, n):
+    return lib().orc_sig_source_advance(phase, phase_inc, n)

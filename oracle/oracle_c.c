@@ -703,3 +703,200 @@ ORC_API void orc_unpack4(const uint8_t *in, int8_t *out, long nbytes)
         out[2 * i + 1] = lut[in[i] & 0x0F];
     }
 }
+
+/* ======================================================================================
+ * SURVEY 8(f) "next" rows: the reference correlators, clComplexFilter, clQuadratureDemod,
+ * clSignalSource.
+ * ====================================================================================== */
+
+/* clXCorrelate ComplexToMag kernel (lib/clXCorrelate_impl.cc:915-929): float fma form */
+ORC_API void orc_xc_mag(const float *a, float *c, long n)
+{
+    for (long i = 0; i < n; i++) c[i] = sqrtf(fmaf(a[2 * i], a[2 * i], a[2 * i + 1] * a[2 * i + 1]));
+}
+
+/* max_shift as the constructor derives it (lib/clXCorrelate_impl.cc:727-747): the search
+ * index (or 0.7 * signal_length made even) rounded UP to a power of two */
+ORC_API int orc_xc_max_shift(int signal_length, int max_search_index)
+{
+    int ms;
+    if (max_search_index > 0) {
+        ms = max_search_index;
+    } else {
+        ms = (int)(0.7f * (float)signal_length);
+        if (ms % 2) ms += 1;
+    }
+    float p2 = log2f((float)ms);
+    int nms = (int)pow(2.0, ceil((double)p2));
+    return nms;
+}
+
+/* kernel XCorrelate (lib/clXCorrelate_impl.cc:851-900): one normalised correlation factor
+ * per shift g - max_shift, g in [0, 2*max_shift); xx/yy are the squared magnitudes
+ * (F32Squared, :976-980); sequential float sums; -2.0 where the overlap has no energy */
+ORC_API void orc_xc_factors(const float *ref, const float *sig, int L, int max_shift, float *factors)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int g = 0; g < 2 * max_shift; g++) {
+        int shift = g - max_shift;
+        int ref_start = shift >= 0 ? shift : -shift;
+        int calc_len = L - ref_start;
+        float sum_xy = 0, sum_x2 = 0, sum_y2 = 0;
+        if (shift > 0) {
+            for (int i = 0; i < calc_len; i++) {
+                sum_xy += ref[ref_start + i] * sig[i];
+                sum_x2 += ref[ref_start + i] * ref[ref_start + i];
+                sum_y2 += sig[i] * sig[i];
+            }
+        } else {
+            for (int i = 0; i < calc_len; i++) {
+                sum_xy += ref[i] * sig[ref_start + i];
+                sum_x2 += ref[i] * ref[i];
+                sum_y2 += sig[ref_start + i] * sig[ref_start + i];
+            }
+        }
+        float denom = sum_x2 * sum_y2;
+        factors[g] = (denom != 0.0f) ? sum_xy / sqrtf(sum_x2 * sum_y2) : -2.0f;
+    }
+}
+
+/* find_max (kernel :1016-1043 + host pass :1371-1413): work-groups of `group` consecutive
+ * entries reduced by a halving tree that replaces slot id by slot id+stride only when
+ * STRICTLY greater, then the first strictly greatest group wins.  Ties therefore go to the
+ * lower SLOT at every level, which is not always the lowest index. */
+ORC_API void orc_xc_find_max(const float *in, int n, int group, float *corr, int *index)
+{
+    int ngroups = n / group;
+    float best = 0;
+    int best_i = 0;
+    float *m = (float *)malloc(sizeof(float) * group);
+    int *l = (int *)malloc(sizeof(int) * group);
+    for (int gi = 0; gi < ngroups; gi++) {
+        for (int k = 0; k < group; k++) {
+            m[k] = in[gi * group + k];
+            l[k] = gi * group + k;
+        }
+        for (int stride = group / 2; stride > 0; stride /= 2)
+            for (int k = 0; k < stride; k++)
+                if (m[k + stride] > m[k]) {
+                    m[k] = m[k + stride];
+                    l[k] = l[k + stride];
+                }
+        if (gi == 0 || m[0] > best) {
+            best = m[0];
+            best_i = l[0];
+        }
+    }
+    free(m);
+    free(l);
+    *corr = best;
+    *index = best_i;
+}
+
+/* clxcorrelate_fft_vcf::work (lib/clxcorrelate_fft_vcf_impl.cc:1057-1145): per vector,
+ * [forward FFT of both when input_type == 2,] ref * conj(sig) (MultConj :895-906), backward FFT
+ * with scale 1.0 (:727), magnitude (:925-931), halves swapped (:1136-1141) */
+ORC_API int orc_xcorr_fft_vcf(const float *ref, const float *sig, float *out, int n, long nvec, int input_type)
+{
+    orc_fft_plan *p = fft_plan_make(n);
+    if (!p) return -1;
+    int h = n / 2;
+#pragma omp parallel
+    {
+        float *a = (float *)malloc(sizeof(float) * 2 * n);
+        float *b = (float *)malloc(sizeof(float) * 2 * n);
+        float *c = (float *)malloc(sizeof(float) * 2 * n);
+#pragma omp for schedule(static)
+        for (long v = 0; v < nvec; v++) {
+            const float *r = ref + 2 * (size_t)n * v, *s = sig + 2 * (size_t)n * v;
+            if (input_type == 2) {
+                memcpy(c, r, sizeof(float) * 2 * n);
+                fft_exec(p, c, a, -1);
+                memcpy(c, s, sizeof(float) * 2 * n);
+                fft_exec(p, c, b, -1);
+            } else {
+                memcpy(a, r, sizeof(float) * 2 * n);
+                memcpy(b, s, sizeof(float) * 2 * n);
+            }
+            for (int i = 0; i < n; i++) {
+                float a_r = a[2 * i], a_i = a[2 * i + 1], b_r = b[2 * i], b_i = -b[2 * i + 1];
+                c[2 * i] = (a_r * b_r) - (a_i * b_i);
+                c[2 * i + 1] = (a_r * b_i) + (a_i * b_r);
+            }
+            fft_exec(p, c, a, +1);
+            float *y = out + (size_t)n * v;
+            for (int i = 0; i < n; i++) {
+                float m = sqrtf(fmaf(a[2 * i], a[2 * i], a[2 * i + 1] * a[2 * i + 1]));
+                y[(i + h) % n] = m;
+            }
+        }
+        free(a);
+        free(b);
+        free(c);
+    }
+    fft_plan_free(p);
+    return 0;
+}
+
+/* clComplexFilter td_FIR_complex_complex (lib/clComplexFilter_impl.cc:805-829): complex taps,
+ * out[g] = sum_{i<K} taps[K-1-i] * in[g+i], in[0] is K-1 samples old (set_history); decimation
+ * keeps every D-th output as the host loop of clFilter does.  Returns outputs written. */
+ORC_API long orc_fir_ccc(const float *in, float *out, long nin, const float *taps, int K, int D)
+{
+    long nfull = nin - (K - 1);
+    long nout = 0;
+    for (long g = 0; g < nfull; g += D, nout++) {
+        float re = 0.0f, im = 0.0f;
+        for (int i = 0; i < K; i++) {
+            float a_r = taps[2 * (K - 1 - i)], a_i = taps[2 * (K - 1 - i) + 1];
+            float b_r = in[2 * (g + i)], b_i = in[2 * (g + i) + 1];
+            re += (a_r * b_r) - (a_i * b_i);
+            im += (a_r * b_i) + (a_i * b_r);
+        }
+        out[2 * nout] = re;
+        out[2 * nout + 1] = im;
+    }
+    return nout;
+}
+
+/* clQuadratureDemod quadDemod, double + fma branch (lib/clQuadratureDemod_impl.cc:126-143):
+ * out[i] = gain * atan2(Im, Re) of in[i+1] * conj(in[i]); in holds n+1 samples (set_history(2)) */
+ORC_API void orc_quad_demod(const float *in, float *out, long n, float gain)
+{
+    for (long i = 0; i < n; i++) {
+        double a_r = in[2 * (i + 1)], a_i = in[2 * (i + 1) + 1];
+        double b_r = in[2 * i], b_i = -1.0 * in[2 * i + 1];
+        double re = fma(a_r, b_r, -(a_i * b_i));
+        double im = fma(a_r, b_i, a_i * b_r);
+        out[i] = (gain != 1.0f) ? (float)((double)gain * atan2(im, re)) : (float)atan2(im, re);
+    }
+}
+
+/* clSignalSource sig_float / sig_complex, double branch (lib/clSignalSource_impl.cc:128-211):
+ * dval = phase + phase_inc * index; waveform 0 = cos, 1 = sin (float) or (cos, sin) (complex) */
+ORC_API void orc_sig_source(float *out, long n, int complex_out, int waveform_sin, double phase, double phase_inc,
+                            double ampl)
+{
+    for (long i = 0; i < n; i++) {
+        double d = phase + phase_inc * (double)i;
+        if (complex_out) {
+            out[2 * i] = (float)(cos(d) * ampl);
+            out[2 * i + 1] = (float)(sin(d) * ampl);
+        } else {
+            out[i] = (float)((waveform_sin ? sin(d) : cos(d)) * ampl);
+        }
+    }
+}
+
+/* phase bookkeeping after a call (lib/clSignalSource_impl.cc:386-398): advance by
+ * inc * (float)n and wrap into (-2pi, 2pi) by dropping whole turns */
+ORC_API double orc_sig_source_advance(double phase, double phase_inc, long n)
+{
+    const double two_pi = 6.28318530717958647692;
+    phase = phase + (phase_inc * (float)n);
+    if (phase > two_pi || phase < -two_pi) {
+        phase = phase / two_pi - (double)((int)(phase / two_pi));
+        phase = phase * two_pi;
+    }
+    return phase;
+}
