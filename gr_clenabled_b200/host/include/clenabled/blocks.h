@@ -131,6 +131,56 @@ public:
                      bool disable_output = false, int pipeline_integration = 0);
 };
 
+// ---- SURVEY 8(f) "next" rows ------------------------------------------------------------------
+// include/clenabled/clXCorrelate.h:56-57; message port "corr" carries the (corrvect, corrective_lags) dict
+class CLENABLED_API clXCorrelate : virtual public gr::sync_block
+{
+public:
+    typedef std::shared_ptr<clXCorrelate> sptr;
+    static sptr make(int openCLPlatformType, int devSelector, int platformId, int devId, bool setDebug,
+                     int num_inputs, int signal_length, int data_type, int data_size, int max_search_index,
+                     int decim_frames, bool async = false);
+};
+
+// include/clenabled/clxcorrelate_fft_vcf.h:49
+class CLENABLED_API clxcorrelate_fft_vcf : virtual public gr::sync_block
+{
+public:
+    typedef std::shared_ptr<clxcorrelate_fft_vcf> sptr;
+    static sptr make(int fftSize, int num_inputs, int openCLPlatformType, int devSelector, int platformId,
+                     int devId, int input_type = 1);
+};
+
+// include/clenabled/clComplexFilter.h:706
+class CLENABLED_API clComplexFilter : virtual public gr::sync_decimator
+{
+public:
+    typedef std::shared_ptr<clComplexFilter> sptr;
+    static sptr make(int openclPlatform, int devSelector, int platformId, int devId, int decimation,
+                     const std::vector<gr_complex> &taps, int nthreads = 1, int setDebug = 0);
+    virtual void set_taps2(const std::vector<gr_complex> &taps) = 0;
+};
+
+// include/clenabled/clQuadratureDemod.h:49
+class CLENABLED_API clQuadratureDemod : virtual public gr::sync_block
+{
+public:
+    typedef std::shared_ptr<clQuadratureDemod> sptr;
+    static sptr make(float gain, int openCLPlatformType, int devSelector, int platformId, int devId,
+                     int setDebug = 0);
+};
+
+// include/clenabled/clSignalSource.h:49-50; waveform SIGSOURCE_COS 1 / SIGSOURCE_SIN 2
+#define SIGSOURCE_COS 1
+#define SIGSOURCE_SIN 2
+class CLENABLED_API clSignalSource : virtual public gr::sync_block
+{
+public:
+    typedef std::shared_ptr<clSignalSource> sptr;
+    static sptr make(int idataType, int openCLPlatformType, int devSelector, int platformId, int devId,
+                     double samp_rate, int waveform, double freq, float amplitude, int setDebug = 0);
+};
+
 } // namespace clenabled
 } // namespace gr
 #endif

@@ -426,6 +426,134 @@ public:
     }
 };
 
+// ------------------------------------------------------------------ clXCorrelate --
+// lib/clXCorrelate_impl.cc:701-842 (ctor), :1528-1594 (synchronous work path)
+class clXCorrelate_impl : public clXCorrelate
+{
+    Handle d;
+    int d_num_inputs, d_signal_length, d_decim_frames, d_frame = 1;
+    std::vector<float> d_corr;
+    std::vector<int32_t> d_lag;
+
+public:
+    clXCorrelate_impl(int dev, int num_inputs, int signal_length, int data_type, int data_size, int max_search_index,
+                      int decim_frames)
+        : gr::sync_block("clXCorrelate", gr::io_signature::make(2, num_inputs, data_size),
+                         gr::io_signature::make(0, 0, 0)),
+          d_num_inputs(num_inputs), d_signal_length(signal_length), d_decim_frames(decim_frames)
+    {
+        if (data_size == 0) throw std::invalid_argument("clXCorrelate: Unknown data type.");     // :710-714
+        must(clb200_xcorrelate_create(dev, num_inputs, signal_length, data_type, max_search_index, &d.h));
+        d_corr.resize(num_inputs - 1);
+        d_lag.resize(num_inputs - 1);
+        set_output_multiple(signal_length);                                                       // :839
+        message_port_register_out(pmt::mp("corr"));                                               // :840
+    }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &) override
+    {
+        if (noutput_items < d_signal_length) return 0;                                            // :1532-1534
+        if (d_decim_frames > 1) {                                                                 // :1539-1547
+            if ((d_frame++ % d_decim_frames) == 0) d_frame = 1;
+            else return d_signal_length;
+        }
+        if (clb200_xcorrelate_work(d.h, in.data(), d_corr.data(), d_lag.data()) != CLB200_OK)
+            return work_failed("clXCorrelate");
+        pmt::pmt_t meta = pmt::make_dict();                                                       // :1585-1593
+        meta = pmt::dict_add(meta, pmt::mp("corrvect"), pmt::init_f32vector(d_corr.size(), d_corr.data()));
+        meta = pmt::dict_add(meta, pmt::mp("corrective_lags"), pmt::init_s32vector(d_lag.size(), d_lag.data()));
+        message_port_pub(pmt::mp("corr"), pmt::cons(meta, pmt::PMT_NIL));
+        return d_signal_length;
+    }
+};
+
+// ----------------------------------------------------------- clxcorrelate_fft_vcf --
+// lib/clxcorrelate_fft_vcf_impl.cc:699-750, :1057-1145: items are whole vectors of fftSize
+class clxcorrelate_fft_vcf_impl : public clxcorrelate_fft_vcf
+{
+    Handle d;
+
+public:
+    clxcorrelate_fft_vcf_impl(int dev, int fftSize, int num_inputs, int input_type)
+        : gr::sync_block("clxcorrelate_fft_vcf", gr::io_signature::make(2, num_inputs, sizeof(gr_complex) * fftSize),
+                         gr::io_signature::make(1, num_inputs - 1, sizeof(float) * fftSize))
+    {
+        must(clb200_xcorr_fft_create(fftSize, num_inputs, input_type, dev, &d.h));
+    }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_xcorr_fft_work(d.h, in.data(), out.data(), noutput_items) != CLB200_OK)
+            return work_failed("clxcorrelate_fft_vcf");
+        return noutput_items;
+    }
+};
+
+// --------------------------------------------------------------- clComplexFilter --
+class clComplexFilter_impl : public clComplexFilter
+{
+    Handle d;
+
+public:
+    clComplexFilter_impl(int dev, int decimation, const std::vector<gr_complex> &taps)
+        : gr::sync_decimator("clComplexFilter", gr::io_signature::make(1, 1, sizeof(gr_complex)),
+                             gr::io_signature::make(1, 1, sizeof(gr_complex)), decimation)
+    {
+        must(clb200_cfilter_create(dev, decimation, reinterpret_cast<const float *>(taps.data()), (int)taps.size(), &d.h));
+        // history lives in the handle (see clFilter_impl above): in[0] is the first NEW sample
+    }
+    void set_taps2(const std::vector<gr_complex> &taps) override
+    {
+        if (clb200_cfilter_set_taps(d.h, reinterpret_cast<const float *>(taps.data()), (int)taps.size()) != CLB200_OK)
+            throw std::invalid_argument(clb200_last_error());
+    }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        long n_out = 0;
+        if (clb200_cfilter_work(d.h, in[0], (long)noutput_items * decimation(), out[0], &n_out) != CLB200_OK)
+            return work_failed("clComplexFilter");
+        return (int)n_out;
+    }
+};
+
+// ------------------------------------------------------------- clQuadratureDemod --
+class clQuadratureDemod_impl : public clQuadratureDemod
+{
+    Handle d;
+
+public:
+    clQuadratureDemod_impl(int dev, float gain)
+        : gr::sync_block("clQuadratureDemod", gr::io_signature::make(1, 1, sizeof(gr_complex)),
+                         gr::io_signature::make(1, 1, sizeof(float)))
+    {
+        must(clb200_quaddemod_create(dev, gain, &d.h));
+        set_output_multiple(32);        // lib/clQuadratureDemod_impl.cc:71; the previous sample lives in the handle
+    }
+    int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
+    {
+        if (clb200_quaddemod_work(d.h, in[0], out[0], noutput_items) != CLB200_OK)
+            return work_failed("clQuadratureDemod");
+        return noutput_items;
+    }
+};
+
+// ---------------------------------------------------------------- clSignalSource --
+class clSignalSource_impl : public clSignalSource
+{
+    Handle d;
+
+public:
+    clSignalSource_impl(int dev, int idataType, double samp_rate, int waveform, double freq, float amplitude)
+        : gr::sync_block("clSignalSource", gr::io_signature::make(0, 0, 0),
+                         gr::io_signature::make(1, 1, item_size(idataType)))
+    {
+        must(clb200_sigsource_create(dev, idataType, samp_rate, waveform, freq, amplitude, &d.h));
+    }
+    int work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &out) override
+    {
+        if (clb200_sigsource_work(d.h, out[0], noutput_items) != CLB200_OK) return work_failed("clSignalSource");
+        return noutput_items;
+    }
+};
+
 } // namespace
 
 // ---------------------------------------------------------------- factories --
@@ -495,6 +623,34 @@ clXEngine::sptr clXEngine::make(int plat, int sel, int pid, int did, bool, int d
         pick_device(plat, sel, pid, did), data_type, polarization, num_inputs, num_channels, integration,
         disable_output, pipeline_integration, output_file, file_base, rollover_size_mb, antenna_list, sync_timestamp,
         object_name, first_channel, starting_chan_center_freq, channel_width));
+}
+
+clXCorrelate::sptr clXCorrelate::make(int plat, int sel, int pid, int did, bool, int num_inputs, int signal_length,
+                                      int data_type, int data_size, int max_search_index, int decim_frames, bool)
+{
+    return gnuradio::get_initial_sptr(new clXCorrelate_impl(pick_device(plat, sel, pid, did), num_inputs, signal_length,
+                                                            data_type, data_size, max_search_index, decim_frames));
+}
+clxcorrelate_fft_vcf::sptr clxcorrelate_fft_vcf::make(int fftSize, int num_inputs, int plat, int sel, int pid, int did,
+                                                      int input_type)
+{
+    return gnuradio::get_initial_sptr(
+        new clxcorrelate_fft_vcf_impl(pick_device(plat, sel, pid, did), fftSize, num_inputs, input_type));
+}
+clComplexFilter::sptr clComplexFilter::make(int plat, int sel, int pid, int did, int decimation,
+                                            const std::vector<gr_complex> &taps, int, int)
+{
+    return gnuradio::get_initial_sptr(new clComplexFilter_impl(pick_device(plat, sel, pid, did), decimation, taps));
+}
+clQuadratureDemod::sptr clQuadratureDemod::make(float gain, int plat, int sel, int pid, int did, int)
+{
+    return gnuradio::get_initial_sptr(new clQuadratureDemod_impl(pick_device(plat, sel, pid, did), gain));
+}
+clSignalSource::sptr clSignalSource::make(int idataType, int plat, int sel, int pid, int did, double samp_rate,
+                                          int waveform, double freq, float amplitude, int)
+{
+    return gnuradio::get_initial_sptr(
+        new clSignalSource_impl(pick_device(plat, sel, pid, did), idataType, samp_rate, waveform, freq, amplitude));
 }
 
 } // namespace clenabled

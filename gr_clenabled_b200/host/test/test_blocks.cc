@@ -181,6 +181,71 @@ int main()
             CHECK(t.find("\"data_type\":\"cf32_le\"") != std::string::npos);
         }
     }
+    // --- clXCorrelate: a copy delayed by 5 samples -> corrective lag -5, published on port "corr"
+    {
+        const int L = 512, MS = 64;
+        std::vector<float> ref(L), sig(L);
+        for (int i = 0; i < L; i++) ref[i] = 0.1f + (float)((i * 2654435761u) >> 20 & 1023) / 1024.0f;
+        for (int i = 0; i < L; i++) sig[i] = i >= 5 ? ref[i - 5] : 0.3f;
+        auto blk = clXCorrelate::make(GPU, FIRST, 0, 0, false, 2, L, DTYPE_FLOAT, sizeof(float), MS, 1);
+        gr_vector_const_void_star iv{ref.data(), sig.data()};
+        gr_vector_void_star ov;
+        CHECK(blk->output_multiple() == L);
+        CHECK(blk->work(L - 1, iv, ov) == 0);
+        CHECK(blk->work(L, iv, ov) == L);
+        auto &msgs = blk->published("corr");
+        CHECK(msgs.size() == 1);
+        if (!msgs.empty()) {
+            pmt::pmt_t meta = pmt::car(msgs[0]);
+            auto lags = pmt::s32vector_elements(pmt::dict_ref(meta, pmt::mp("corrective_lags"), pmt::PMT_NIL));
+            auto corr = pmt::f32vector_elements(pmt::dict_ref(meta, pmt::mp("corrvect"), pmt::PMT_NIL));
+            CHECK(lags.size() == 1 && lags[0] == -5);
+            CHECK(corr.size() == 1 && corr[0] > 0.99f);
+        }
+        CHECK(throws<std::invalid_argument>([&] { clXCorrelate::make(GPU, FIRST, 0, 0, false, 2, 511, DTYPE_FLOAT, 4, MS, 1); }));
+        CHECK(throws<std::invalid_argument>([&] { clXCorrelate::make(GPU, FIRST, 0, 0, false, 2, L, DTYPE_FLOAT, 0, MS, 1); }));
+    }
+    // --- clxcorrelate_fft_vcf on time series: circular delay of 3 -> peak at N/2 - 3
+    {
+        const int N = 256;
+        std::vector<gr_complex> a(N), b(N);
+        for (int i = 0; i < N; i++) a[i] = gr_complex((float)((i * 2654435761u) >> 20 & 1023) / 512.0f - 1.0f, (float)((i * 40503u) & 255) / 128.0f - 1.0f);
+        for (int i = 0; i < N; i++) b[i] = a[(i + N - 3) % N];
+        auto blk = clxcorrelate_fft_vcf::make(N, 2, GPU, FIRST, 0, 0, 2);
+        std::vector<float> out(N);
+        gr_vector_const_void_star iv{a.data(), b.data()};
+        gr_vector_void_star ov{out.data()};
+        CHECK(blk->work(1, iv, ov) == 1);
+        int best = 0;
+        for (int i = 1; i < N; i++)
+            if (out[i] > out[best]) best = i;
+        CHECK(best == N / 2 - 3);
+    }
+    // --- clComplexFilter: an impulse returns the taps; clQuadratureDemod: constant rotation; clSignalSource
+    {
+        std::vector<gr_complex> taps{{1, 2}, {3, -1}, {0.5f, 0.25f}};
+        auto blk = clComplexFilter::make(GPU, FIRST, 0, 0, 1, taps);
+        std::vector<gr_complex> in(64, gr_complex(0, 0)), out(64);
+        in[0] = gr_complex(1, 0);
+        gr_vector_const_void_star iv{in.data()};
+        gr_vector_void_star ov{out.data()};
+        CHECK(blk->work(64, iv, ov) == 64);
+        CHECK(out[0] == taps[0] && out[1] == taps[1] && out[2] == taps[2] && out[3] == gr_complex(0, 0));
+        auto qd = clQuadratureDemod::make(2.0f, GPU, FIRST, 0, 0);
+        std::vector<gr_complex> tone(1024);
+        for (int i = 0; i < 1024; i++) tone[i] = std::polar(1.0f, 0.25f * (float)i);
+        std::vector<float> ph(1024);
+        gr_vector_const_void_star qi{tone.data()};
+        gr_vector_void_star qo{ph.data()};
+        CHECK(qd->work(1024, qi, qo) == 1024);
+        CHECK(std::fabs(ph[10] - 0.5f) < 1e-4f && std::fabs(ph[1023] - 0.5f) < 1e-4f);
+        auto src = clSignalSource::make(DTYPE_COMPLEX, GPU, FIRST, 0, 0, 1000.0, SIGSOURCE_COS, 10.0, 2.0f);
+        std::vector<gr_complex> s(100);
+        gr_vector_const_void_star none;
+        gr_vector_void_star so{s.data()};
+        CHECK(src->work(100, none, so) == 100);
+        CHECK(std::abs(s[25] - std::polar(2.0f, (float)(2.0 * M_PI * 10.0 / 1000.0 * 25))) < 1e-5f);
+    }
     if (failures == 0) printf("ALL OK\n");
     return failures == 0 ? 0 : 1;
 }

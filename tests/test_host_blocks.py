@@ -18,7 +18,8 @@ def test_block_library_is_built_and_links_the_c_abi():
     # the factories the reference exports (mangled gr::clenabled::<Block>::make)
     syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
     for blk in ("clMathConst", "clMathOp", "clFFT", "clFilter", "clPolyphaseChannelizer", "clXEngine",
-                "clLog", "clSNR", "clComplexToMag", "clComplexToArg", "clComplexToMagPhase", "clMagPhaseToComplex"):
+                "clLog", "clSNR", "clComplexToMag", "clComplexToArg", "clComplexToMagPhase", "clMagPhaseToComplex",
+                "clXCorrelate", "clxcorrelate_fft_vcf", "clComplexFilter", "clQuadratureDemod", "clSignalSource"):
         assert ("9clenabled%d%s4make" % (len(blk), blk)) in syms, blk
     assert lib is not None
 
