@@ -8,6 +8,7 @@
 #define CLB200_GR_STUB_BLOCK_H
 #include <complex>
 #include <functional>
+#include <cstdint>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -44,6 +45,12 @@ public:
 private:
     io_signature(int mn, int mx, int sz) : d_min(mn), d_max(mx), d_size(sz) {}
     int d_min, d_max, d_size;
+};
+
+// stream tag (gnuradio/tags.h): absolute offset, key, value
+struct tag_t {
+    uint64_t offset = 0;
+    pmt::pmt_t key, value;
 };
 
 class block
@@ -86,6 +93,32 @@ public:
     int consumed_each() const { return d_consumed_each; }
     const std::vector<int> &consumed() const { return d_consumed; }
 
+    // tags of input `port` whose offset RELATIVE to the current window lies in [start, end)
+    // (block::get_tags_in_window, used by the X-engine's ATA synchroniser, lib/clXEngine_impl.cc:1170-1172)
+    void get_tags_in_window(std::vector<tag_t> &v, unsigned port, uint64_t start, uint64_t end)
+    {
+        v.clear();
+        if (port >= d_tags.size()) return;
+        const uint64_t base = port < d_read.size() ? d_read[port] : 0;
+        for (auto &t : d_tags[port])
+            if (t.offset >= base + start && t.offset < base + end) v.push_back(t);
+    }
+    // test access: what the upstream block / the scheduler would do
+    void test_add_tag(unsigned port, uint64_t abs_offset, pmt::pmt_t key, pmt::pmt_t value)
+    {
+        if (d_tags.size() <= port) d_tags.resize(port + 1);
+        tag_t t;
+        t.offset = abs_offset;
+        t.key = key;
+        t.value = value;
+        d_tags[port].push_back(t);
+    }
+    void test_set_read_offset(unsigned port, uint64_t abs_offset)
+    {
+        if (d_read.size() <= port) d_read.resize(port + 1, 0);
+        d_read[port] = abs_offset;
+    }
+
     void message_port_register_out(pmt::pmt_t id) { d_ports[pmt::symbol_to_string(id)]; }
     void message_port_pub(pmt::pmt_t id, pmt::pmt_t msg) { d_ports[pmt::symbol_to_string(id)].push_back(msg); }
     std::vector<pmt::pmt_t> &published(const std::string &port) { return d_ports[port]; }
@@ -105,6 +138,8 @@ private:
     int d_output_multiple = 1, d_max_noutput = 0, d_consumed_each = 0;
     double d_rate = 1.0;
     std::vector<int> d_consumed;
+    std::vector<std::vector<tag_t>> d_tags;
+    std::vector<uint64_t> d_read;
     std::map<std::string, std::vector<pmt::pmt_t>> d_ports;
 };
 

@@ -297,6 +297,9 @@ class clXEngine_impl : public clXEngine
     int d_rollover_index = 0, d_first_channel;
     double d_chan_freq, d_chan_width;
     FILE *d_fp = nullptr;
+    bool d_use_sync, d_synchronized = false;      // ATA SNAP tag synchroniser (:1158-1226)
+    uint64_t d_current_timestamp = 0;
+    std::vector<uint64_t> d_tag_list;
 
     bool open_file()
     {
@@ -343,7 +346,8 @@ public:
     clXEngine_impl(int dev, int data_type, int polarization, int num_inputs, int num_channels, int integration,
                    bool disable_output, int pipeline_integration, bool output_file, const std::string &file_base,
                    int rollover_size_mb, const std::vector<std::string> &antenna_list, long sync_timestamp,
-                   const std::string &object_name, int first_channel, double chan_freq, double chan_width)
+                   const std::string &object_name, int first_channel, double chan_freq, double chan_width,
+                   bool internal_synchronizer)
         : gr::block("clXEngine",
                     gr::io_signature::make(2, num_inputs * (data_type == DTYPE_PACKEDXY ? 1 : polarization),
                                            num_channels * (data_type == DTYPE_PACKEDXY ? 2
@@ -354,8 +358,12 @@ public:
           d_integration(integration), d_pipeline(pipeline_integration), d_disable_output(disable_output),
           d_output_file(output_file), d_file_base(file_base), d_object_name(object_name), d_antennas(antenna_list),
           d_rollover_bytes((long)rollover_size_mb * 1000000L), d_sync_timestamp(sync_timestamp),
-          d_first_channel(first_channel), d_chan_freq(chan_freq), d_chan_width(chan_width)
+          d_first_channel(first_channel), d_chan_freq(chan_freq), d_chan_width(chan_width),
+          d_use_sync(internal_synchronizer)
     {
+        if (internal_synchronizer && (integration % 16) > 0)          // :111-116
+            throw std::out_of_range("ATA xengine: The number of integration frames should be a multiple of 16 to "
+                                    "align with blocks coming from the SNAP.");
         must(clb200_xengine_create(dev, data_type, polarization, num_inputs, num_channels, integration, &d.h),
              num_inputs < 2);                   // std::out_of_range, clXEngine_impl.cc:106-109
         d_sample_bytes = data_type == DTYPE_COMPLEX ? sizeof(gr_complex) : (data_type == DTYPE_BYTE ? 2 : 1);
@@ -363,6 +371,11 @@ public:
         d_matrix.resize((size_t)clb200_xengine_output_items(d.h));
         message_port_register_out(pmt::mp("xcorr"));                 // :294-295
         message_port_register_out(pmt::mp("sync"));
+        if (d_use_sync) {                                            // :297-301
+            set_tag_propagation_policy(TPP_DONT);
+            set_output_multiple(16);
+            d_tag_list.resize(num_inputs * (data_type == DTYPE_PACKEDXY ? 1 : polarization));
+        }
     }
     ~clXEngine_impl() override
     {
@@ -385,6 +398,31 @@ public:
     int general_work(int noutput_items, gr_vector_int &, gr_vector_const_void_star &in, gr_vector_void_star &) override
     {
         gr::thread::scoped_lock guard(d_setlock);
+        if (d_use_sync && !d_synchronized) {
+            // SNAP packets carry a sequence tag on every 16-step block (t[n+1] = t[n] + 16).  Until the first
+            // tag of every input is the same, drop (highest - own) items from each input and produce nothing.
+            uint64_t highest = 0, first = 0;
+            bool in_sync = true;
+            for (size_t p = 0; p < d_tag_list.size(); p++) {
+                std::vector<gr::tag_t> tags;
+                get_tags_in_window(tags, (unsigned)p, 0, 1);
+                if (tags.empty()) return 0;                    // (the reference would dereference tags[0])
+                const uint64_t t0 = pmt::to_uint64(tags[0].value);
+                if (p == 0) first = t0;
+                else if (t0 != first) in_sync = false;
+                d_tag_list[p] = t0;
+                highest = std::max(highest, t0);
+            }
+            if (!in_sync) {
+                for (size_t p = 0; p < d_tag_list.size(); p++)
+                    consume((int)p, (int)std::min<uint64_t>(highest - d_tag_list[p], (uint64_t)noutput_items));
+                return 0;
+            }
+            d_synchronized = true;
+            d_current_timestamp = highest;
+            d_sync_timestamp = (long)highest;                   // goes into the JSON sidecar (write_json(highest_tag))
+            message_port_pub(pmt::mp("sync"), pmt::cons(pmt::intern("synctimestamp"), pmt::from_uint64(highest)));
+        }
         int n = std::min(noutput_items, d_integration - d_tracker);
         const size_t vec = (size_t)d_num_channels * d_sample_bytes;          // bytes of one port item
         const size_t row = vec * d_npol;                                      // one station, one time step
@@ -615,14 +653,14 @@ clPolyphaseChannelizer::sptr clPolyphaseChannelizer::make(int plat, int sel, int
 clXEngine::sptr clXEngine::make(int plat, int sel, int pid, int did, bool, int data_type, int polarization,
                                 int num_inputs, int, int first_channel, int num_channels, int integration,
                                 std::vector<std::string> antenna_list, bool output_file, std::string file_base,
-                                int rollover_size_mb, bool, long sync_timestamp, std::string object_name,
+                                int rollover_size_mb, bool internal_synchronizer, long sync_timestamp, std::string object_name,
                                 double starting_chan_center_freq, double channel_width, bool disable_output,
                                 int pipeline_integration)
 {
     return gnuradio::get_initial_sptr(new clXEngine_impl(
         pick_device(plat, sel, pid, did), data_type, polarization, num_inputs, num_channels, integration,
         disable_output, pipeline_integration, output_file, file_base, rollover_size_mb, antenna_list, sync_timestamp,
-        object_name, first_channel, starting_chan_center_freq, channel_width));
+        object_name, first_channel, starting_chan_center_freq, channel_width, internal_synchronizer));
 }
 
 clXCorrelate::sptr clXCorrelate::make(int plat, int sel, int pid, int did, bool, int num_inputs, int signal_length,

@@ -181,6 +181,29 @@ int main()
             CHECK(t.find("\"data_type\":\"cf32_le\"") != std::string::npos);
         }
     }
+    // --- clXEngine ATA synchroniser (lib/clXEngine_impl.cc:1158-1226): inputs whose first SNAP sequence tags differ
+    //     are trimmed to the highest tag; once equal, "synctimestamp" is published and data flows
+    {
+        const int A = 2, F = 4, T = 16;
+        CHECK(throws<std::out_of_range>([&] { clXEngine::make(GPU, FIRST, 0, 0, false, DTYPE_BYTE, 1, A, 1, 0, F, 24, {}, false, "", 0, true); }));
+        auto blk = clXEngine::make(GPU, FIRST, 0, 0, false, DTYPE_BYTE, 1, A, 1, 0, F, T, {}, false, "", 0, true);
+        CHECK(blk->output_multiple() == 16);
+        std::vector<int8_t> a(T * F * 2, 1), b(T * F * 2, 1);
+        gr_vector_const_void_star iv{a.data(), b.data()};
+        gr_vector_void_star ov;
+        gr_vector_int ni{T, T};
+        blk->test_add_tag(0, 0, pmt::mp("seq"), pmt::from_uint64(1000));
+        blk->test_add_tag(1, 0, pmt::mp("seq"), pmt::from_uint64(1016));
+        CHECK(blk->general_work(T, ni, iv, ov) == 0);
+        CHECK(blk->consumed().size() == 2 && blk->consumed()[0] == 16 && blk->consumed()[1] == 0);
+        CHECK(blk->published("sync").empty());
+        blk->test_set_read_offset(0, 16);                         // the scheduler advanced input 0 by 16 items
+        blk->test_add_tag(0, 16, pmt::mp("seq"), pmt::from_uint64(1016));
+        CHECK(blk->general_work(T, ni, iv, ov) == T);
+        CHECK(blk->published("sync").size() == 1);
+        if (!blk->published("sync").empty()) CHECK(pmt::to_uint64(pmt::cdr(blk->published("sync")[0])) == 1016);
+        CHECK(blk->published("xcorr").size() == 1);
+    }
     // --- clXCorrelate: a copy delayed by 5 samples -> corrective lag -5, published on port "corr"
     {
         const int L = 512, MS = 64;
