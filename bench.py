@@ -263,6 +263,75 @@ def secondary_blocks(torch, blocks, capi, dev, stream_ptr, hbm_peak):
     return out
 
 
+def cpu_blocks(cores):
+    """The reference CPU path of the other BASELINE configs, restated by the oracle, each on a bounded
+    sample (~1-2 s): the Msamples/s that sit beside the device-resident `blocks` figures."""
+    import numpy as np
+    from oracle import oracle as orc
+    res = {}
+
+    def rate(fn, nsamp, min_s=1.0):
+        fn()
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            fn()
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_s:
+                return nsamp * reps / dt / 1e6
+
+    try:
+        orc.lib().orc_set_threads(1)                       # clFilter's CPU paths are single-threaded (nthreads ignored)
+        taps = np.zeros(256, np.float32)
+        taps[:255] = orc.firdes_low_pass_hamming(1.0, 30e6, 1.5e6, 283000.0)
+        n = 257 * 2048
+        x = orc.rng_c32(n, orc.SEED_L)
+        f = orc.lib().orc_fftfilt_create(taps, 256, 1)
+        out = np.zeros(n, np.complex64)
+        res["clFilter_fft_256tap"] = {"Msamples_s": rate(lambda: orc.lib().orc_fftfilt_filter(f, n, orc._f(x), orc._f(out)), n),
+                                      "cores": 1, "what": "fft_filter_ccf::filter restated (fftsize 512 / 257 new samples)"}
+        orc.lib().orc_fftfilt_destroy(f)
+        xh = orc.rng_c32(1 << 16, orc.SEED_L)
+        res["clFilter_fir_256tap"] = {"Msamples_s": rate(lambda: orc.fir(xh, taps, 1), xh.size - 255), "cores": 1,
+                                      "what": "fir_filter_ccf::filterN restated"}
+        orc.lib().orc_set_threads(cores)
+        M = 64
+        ptaps = np.zeros(128, np.float32)
+        ptaps[:127] = orc.firdes_low_pass_hamming(1.0, 64.0, 0.5, 1.21)
+        niter = 8192
+        xp = orc.rng_c32((niter - 1) * M + 128, orc.SEED_P)
+        res["clPolyphaseChannelizer_64ch"] = {"Msamples_s": rate(lambda: orc.pfb(xp, ptaps, M, M, list(range(M)), niter), niter * M),
+                                              "cores": cores, "what": "filterpfb2 + DFT + map restated (the reference has no CPU path)"}
+        A, F, T = 32, 16, 1024
+        buf = orc.rng_i8(T * A * F * 2, orc.SEED_X)
+        res["clXEngine_32st_int1024"] = {"Msamples_s": rate(lambda: orc.xengine_f32(buf, A, F, T, 1), A * F * T),
+                                         "cores": cores, "what": "CharToComplex + XCorrelate restated on a 16-channel slab "
+                                                                  "(the reference has no CPU X-engine)"}
+    except Exception as e:                               # noqa: BLE001
+        res["error"] = str(e)
+    return res
+
+
+def xengine_e2e(blocks, capi, dev, torch):
+    """clXEngine through the host entry point (clb200_xengine_work: pinned host integration buffer in,
+    visibilities out), BASELINE config 5 on one GPU."""
+    import numpy as np
+    A, F, T = 32, 1024, 1024
+    nb = T * A * F * 2
+    src = torch.randint(-127, 128, (nb,), dtype=torch.int8).pin_memory()
+    out = torch.empty(F * (A * (A + 1) // 2) * 2, dtype=torch.float32).pin_memory()
+    blk = blocks.clXEngine(1, 2, 0, dev, False, capi.DTYPE_BYTE, 1, A, 1, 0, F, T, [])
+    lib = capi.load()
+    ip, op = C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr())
+    capi.check(lib.clb200_xengine_work(blk._h, ip, op, 0))
+    reps, t0 = 5, time.perf_counter()
+    for _ in range(reps):
+        capi.check(lib.clb200_xengine_work(blk._h, ip, op, 0))
+    dt = (time.perf_counter() - t0) / reps
+    return {"us_per_integration": dt * 1e6, "Msamples_s": A * F * T / dt / 1e6, "h2d_bytes": nb, "d2h_bytes": out.numel() * 4,
+            "api": "clb200_xengine_work (pinned host in/out)"}
+
+
 def per_call(blocks, capi, dev, n=8192, iters=300):
     """BASELINE configs[0]: scheduler-sized work() calls (8192 gr_complex, pageable host buffers,
     1 warm-up + N timed calls like lib/test_clenabled.cc:1237-1251), through the C ABI."""
@@ -431,6 +500,10 @@ def main():
         torch.cuda.empty_cache()
         extra = secondary_blocks(torch, blocks, capi, local, sp, hbm_peak)
         extra["per_call_8192_pageable"] = per_call(blocks, capi, local)
+        try:
+            extra["clXEngine_e2e_host"] = xengine_e2e(blocks, capi, local, torch)
+        except Exception as e:                           # noqa: BLE001
+            extra["clXEngine_e2e_host"] = {"error": str(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -466,6 +539,8 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
+            if extra is not None:
+                extra["cpu_reference_paths"] = cpu_blocks(cpu["cores"])
         if extra:
             line["blocks"] = extra
         print(json.dumps(line), flush=True)
