@@ -24,7 +24,10 @@ using namespace clb200::fftdev;
 
 namespace {
 
-template <int LOGM, int EPT, int BATCH, int MINB>
+// NT > 0: critically sampled (R == M, the commutator never rotates) with at most NT taps per arm --
+// every thread keeps the taps of its arms in registers for the whole launch, which removes half of
+// the load instructions of the arm loop (the kernel is LSU-bound: 73 % of the L1 wavefront peak).
+template <int LOGM, int EPT, int BATCH, int MINB, int NT>
 __global__ void __launch_bounds__((1 << LOGM) / EPT * BATCH, MINB)
 k_pfb(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
       const float *__restrict__ taps, const float2 *__restrict__ tw, const int *__restrict__ map,
@@ -39,6 +42,16 @@ k_pfb(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
     const int lt = (BATCH == 1) ? threadIdx.x : threadIdx.x % T;
     float2 *buf = smem + tb * LINE;
     const int rot_step = M - R;                 // commutator rotation per time step (mod M)
+    float tr[NT > 0 ? NT : 1][EPT];
+    if (NT > 0) {
+#pragma unroll
+        for (int g = 0; g < NT; g++)
+#pragma unroll
+            for (int e = 0; e < EPT; e++) {
+                const int k = g * M + in_index<P, EPT>(lt, e);
+                tr[g][e] = k < ntaps ? __ldg(taps + k) : 0.f;
+            }
+    }
 
     const long ntile = (niter + BATCH - 1) / BATCH;
     for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
@@ -56,6 +69,22 @@ k_pfb(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
                 j[e] = (in_index<P, EPT>(lt, e) - rot) & (M - 1);
                 x[e] = make_float2(0.f, 0.f);
             }
+            if (NT > 0) {
+#pragma unroll
+                for (int g = 0; g < NT; g++) {
+                    float2 v[EPT];
+#pragma unroll
+                    for (int e = 0; e < EPT; e++) {
+                        const int k = g * M + j[e];
+                        v[e] = k < ntaps ? __ldg(xin - k) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPT; e++) {
+                        x[e].y = fmaf(v[e].x, tr[g][e], x[e].y);
+                        x[e].x = fmaf(v[e].y, tr[g][e], x[e].x);
+                    }
+                }
+            } else
             for (int k0 = 0; k0 < ntaps; k0 += M) {
                 float2 v[EPT];
                 float t[EPT];
@@ -104,7 +133,8 @@ typedef void (*pfb_kernel_t)(const float2 *, float2 *, long, const float *, cons
 struct PfbVariant {
     int logm, batch, threads, smem_bytes;
     void (*fill_tw)(std::vector<float2> &);
-    pfb_kernel_t kernel;
+    pfb_kernel_t kernel;          // any R, any tap count
+    pfb_kernel_t kernel_crit[2];  // R == M and <= 2 / <= 4 taps per arm: taps in registers
 };
 
 template <int LOGM, int EPT>
@@ -128,7 +158,8 @@ PfbVariant make_pfb()
     using P = Plan<LOGM, EPT>;
     constexpr int LINE = (P::SMEM_F2 > P::pad(P::N)) ? P::SMEM_F2 : P::pad(P::N);
     return PfbVariant{LOGM, BATCH, P::T * BATCH, LINE * BATCH * (int)sizeof(float2),
-                      &fill_tw_p<LOGM, EPT>, &k_pfb<LOGM, EPT, BATCH, MINB>};
+                      &fill_tw_p<LOGM, EPT>, &k_pfb<LOGM, EPT, BATCH, MINB, 0>,
+                      {&k_pfb<LOGM, EPT, BATCH, MINB, 2>, &k_pfb<LOGM, EPT, BATCH, MINB, 4>}};
 }
 
 const PfbVariant *pick_pfb(int logm)
@@ -148,6 +179,7 @@ const PfbVariant *pick_pfb(int logm)
 struct Pfb : clb200_block {
     int ntaps = 0, M = 0, R = 0, nmap = 0, buf_items = 0, identity = 0, resident = 1;
     const PfbVariant *var = nullptr;
+    pfb_kernel_t kernel = nullptr;
     Buf d_taps, d_tw, d_map;
     ~Pfb() override
     {
@@ -164,7 +196,7 @@ int pfb_launch(Pfb *p, const void *d_in, void *d_out, long niter, cudaStream_t s
     const PfbVariant *v = p->var;
     long ntile = (niter + v->batch - 1) / v->batch;
     int grid = grid_for(ntile, device_sm_count(p->device), p->resident);
-    v->kernel<<<grid, v->threads, v->smem_bytes, st>>>(
+    p->kernel<<<grid, v->threads, v->smem_bytes, st>>>(
         (const float2 *)d_in, (float2 *)d_out, niter, (const float *)p->d_taps.p,
         (const float2 *)p->d_tw.p, (const int *)p->d_map.p, p->ntaps, p->R, p->nmap, p->identity);
     CLB_CUDA(cudaGetLastError());
@@ -226,12 +258,18 @@ int clb200_pfb_create(int device, const float *taps, int ntaps, int buf_items, i
         set_error("clPolyphaseChannelizer: table upload failed");
         return fail(CLB200_ECUDA);
     }
-    cudaError_t e = cudaFuncSetAttribute((const void *)p->var->kernel,
+    p->kernel = p->var->kernel;
+    {
+        const char *gen = getenv("CLB200_PFB_GENERAL");           // A/B: force the general kernel
+        const int per_arm = (ntaps + M - 1) / M;
+        if (R == M && per_arm <= 4 && !(gen && atoi(gen))) p->kernel = p->var->kernel_crit[per_arm <= 2 ? 0 : 1];
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void *)p->kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          p->var->smem_bytes);
     int occ = 0;
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)p->var->kernel,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)p->kernel,
                                                           p->var->threads, p->var->smem_bytes);
     if (e != cudaSuccess || occ < 1) {
         set_error("clPolyphaseChannelizer: kernel does not fit an SM (%s)", cudaGetErrorString(e));
