@@ -495,6 +495,29 @@ def main():
             "us_per_integration": us, "Msamples_s": A * F * T / us, "gpus": world,
             "collective": "all_gather of %d B visibility slabs per rank (NCCL)" % (slab.numel() * 4),
             "gathered_items": int(full.numel() // 2)}
+        # the same step with the gather fused into the kernel: the epilogue stores this rank's slab into every
+        # rank's full matrix over NVLink peer memory, no collective call
+        try:
+            xg = blocks.clXEngine(1, 2, 0, local, False, capi.DTYPE_BYTE, 1, A, 1, 0, fc, T, [])
+            xg.set_shard(F, f0)
+            pg = multigpu.PeerGather(xg, local, F, nbl)
+            for i in range(3):
+                xg.launch_device_gather(bufs[i % 4].data_ptr(), sp)
+            barrier()
+            x0.record(stream)
+            for i in range(nx):
+                xg.launch_device_gather(bufs[i % 4].data_ptr(), sp)
+            x1.record(stream)
+            barrier()
+            t = torch.tensor([x0.elapsed_time(x1) / nx], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            us2 = float(t.item()) * 1e3
+            extra["clXEngine_32st_1024ch_int1024_sharded_fused_gather"] = {
+                "us_per_integration": us2, "Msamples_s": A * F * T / us2, "gpus": world,
+                "collective": "none: epilogue stores into every rank's matrix (cudaIpc peer memory over NVLink)"}
+            pg.close()
+        except Exception as e:                           # noqa: BLE001
+            extra["clXEngine_32st_1024ch_int1024_sharded_fused_gather"] = {"error": str(e)}
     if rank == 0 and world == 1 and not args.no_blocks:
         del x, y
         torch.cuda.empty_cache()

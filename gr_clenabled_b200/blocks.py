@@ -363,6 +363,13 @@ class clXEngine(_Block):
     def launch_device_i32(self, d_in, d_out, stream=0):
         check(self._lib.clb200_xengine_launch_device_i32(self._h, d_in, d_out, stream))
 
+    def set_gather(self, full_out_ptrs):
+        a = (C.c_void_p * len(full_out_ptrs))(*full_out_ptrs)
+        check(self._lib.clb200_xengine_set_gather(self._h, len(full_out_ptrs), a))
+
+    def launch_device_gather(self, d_in, stream=0):
+        check(self._lib.clb200_xengine_launch_device_gather(self._h, d_in, stream))
+
 
 # ------------------------------------------------------------------------------------------
 # SURVEY 8(f) "next" rows

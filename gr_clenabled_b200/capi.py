@@ -89,6 +89,14 @@ SIGNATURES = {
     "clb200_xengine_launch_device": (_i, [_vp, _vp, _vp, _i, _vp]),
     "clb200_xengine_launch_device_i32": (_i, [_vp, _vp, _vp, _vp]),
     "clb200_xengine_set_shard": (_i, [_vp, _i, _i]),
+    "clb200_xengine_set_gather": (_i, [_vp, _i, _ph]),
+    "clb200_xengine_launch_device_gather": (_i, [_vp, _vp, _vp]),
+    "clb200_mem_alloc": (_i, [_i, C.c_size_t, _ph]),
+    "clb200_mem_free": (_i, [_i, _vp]),
+    "clb200_mem_copy_to_host": (_i, [_i, _vp, _vp, C.c_size_t]),
+    "clb200_ipc_export": (_i, [_i, _vp, _vp]),
+    "clb200_ipc_open": (_i, [_i, _vp, _ph]),
+    "clb200_ipc_close": (_i, [_i, _vp]),
     "clb200_xcorrelate_create": (_i, [_i, _i, _i, _i, _i, _ph]),
     "clb200_xcorrelate_max_shift": (_i, [_vp]),
     "clb200_xcorrelate_work": (_i, [_vp, _ph, _vp, _vp]),

@@ -205,4 +205,52 @@ int clb200_get_counters(clb200_handle h, uint64_t *h2d, uint64_t *d2h, uint64_t 
     return CLB200_OK;
 }
 
+
+// ---- device memory that other ranks of the box can map (fused X-engine gather) ----
+int clb200_mem_alloc(int device, size_t bytes, void **dptr)
+{
+    CLB_CHECK(dptr != nullptr && bytes > 0, CLB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    CLB_CUDA(cudaMalloc(dptr, bytes));
+    CLB_CUDA(cudaMemset(*dptr, 0, bytes));
+    return CLB200_OK;
+}
+int clb200_mem_free(int device, void *dptr)
+{
+    DeviceGuard g(device);
+    CLB_CUDA(cudaFree(dptr));
+    return CLB200_OK;
+}
+int clb200_mem_copy_to_host(int device, const void *dptr, void *host, size_t bytes)
+{
+    DeviceGuard g(device);
+    CLB_CUDA(cudaMemcpy(host, dptr, bytes, cudaMemcpyDeviceToHost));
+    return CLB200_OK;
+}
+int clb200_ipc_export(int device, void *dptr, void *handle64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "interprocess handle is 64 bytes");
+    CLB_CHECK(dptr && handle64, CLB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t h;
+    CLB_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, 64);
+    return CLB200_OK;
+}
+int clb200_ipc_open(int device, const void *handle64, void **dptr)
+{
+    CLB_CHECK(dptr && handle64, CLB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CLB_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CLB200_OK;
+}
+int clb200_ipc_close(int device, void *dptr)
+{
+    DeviceGuard g(device);
+    CLB_CUDA(cudaIpcCloseMemHandle(dptr));
+    return CLB200_OK;
+}
+
 } // extern "C"

@@ -57,6 +57,11 @@ struct XeParams {
     int l2_rows;            // prefetch whole (t, station) rows into L2 ahead of the demand loads
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
+    // fused all-gather (TMA kernel only): the float result also goes to `ngather` full matrices
+    // (this rank's and the peers', peer-mapped) at item offset gather_off
+    float2 *gather[8];
+    int ngather;
+    long gather_off;
 };
 
 // which row tiles warp share Q of WPC owns
@@ -452,6 +457,8 @@ struct XEngine : clb200_block {
     bool use_tc = false;
     bool use_tma = false;              // TMA-fed variant of the tcgen05 kernel (needs 16 B aligned rows)
     int l2promo = 0;
+    void *gather[8] = {};              // full matrices of every rank (clb200_xengine_set_gather)
+    int ngather = 0;
     int fc_override = 0;               // CLB200_XE_FC: channels per CTA of the TMA kernel (8 | 16)
     bool pdl = true;                   // programmatic dependent launch (CLB200_XE_PDL=0 turns it off)
     Buf d_in[2], d_unpacked, d_acc, d_out;
@@ -488,7 +495,7 @@ struct XEngine : clb200_block {
 // enqueue the correlation of `T` time steps held at d_in (layout [t][A][Fstride][npol]);
 // exactly one of out_i32 / out_f32 may be null
 int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32_t *out_i32,
-              float2 *out_f32, int accumulate, cudaStream_t st)
+              float2 *out_f32, int accumulate, cudaStream_t st, bool gather = false)
 {
     const int sms = device_sm_count(x->device);
     if (x->data_type == CLB200_DTYPE_COMPLEX) {
@@ -536,6 +543,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         const char *e = getenv("CLB200_XE_SLICES");       // tuning override: 0 = stream-K split
         if (e && ngroups < 2 * sms && nst > 1) tslices = std::min(nst, atoi(e));
     }
+    if (gather && tslices == 0) tslices = 1;            // whole groups per CTA: no partial sums in memory
     if (tma_ok && tslices > 1) {
         // the slices of a group are the CTAs of one cluster: 2, 4 or 8, each finalising fc/slices channels
         int c = 2;
@@ -578,6 +586,14 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.f_off = f_off;
     p.T = T;
     p.accumulate = accumulate;
+    p.ngather = 0;
+    p.gather_off = 0;
+    if (gather) {
+        CLB_CHECK(tma, CLB200_ESTATE, "clXEngine: the peer-memory gather needs the TMA kernel (16 B aligned rows, <= 32 inputs x pols)");
+        p.ngather = x->ngather;
+        for (int r = 0; r < x->ngather; r++) p.gather[r] = (float2 *)x->gather[r];
+        p.gather_off = (long)x->f_first * x->nbl() * x->npol * x->npol;
+    }
     p.scale = scale;
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
     if (tma) {
@@ -801,6 +817,32 @@ int clb200_xengine_set_shard(clb200_handle h, int total_channels, int chan_first
     x->Ftotal = total_channels;
     x->f_first = chan_first;
     return CLB200_OK;
+}
+
+int clb200_xengine_set_gather(clb200_handle h, int nranks, void *const *full_out_c32)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(nranks >= 1 && nranks <= CLB200_XENGINE_MAX_GATHER && full_out_c32, CLB200_EINVAL,
+              "clXEngine: 1..%d gather destinations, got %d", CLB200_XENGINE_MAX_GATHER, nranks);
+    CLB_CHECK(x->Ftotal > 0, CLB200_ESTATE, "clXEngine: set_shard first");
+    CLB_CHECK(x->data_type != CLB200_DTYPE_COMPLEX, CLB200_EINVAL, "clXEngine: the gather is for the integer input types");
+    for (int r = 0; r < nranks; r++) {
+        CLB_CHECK(full_out_c32[r] != nullptr && ((uintptr_t)full_out_c32[r] % 8) == 0, CLB200_EINVAL, "bad destination %d", r);
+        x->gather[r] = full_out_c32[r];
+    }
+    x->ngather = nranks;
+    return CLB200_OK;
+}
+
+int clb200_xengine_launch_device_gather(clb200_handle h, const void *d_in, void *stream)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(x->ngather > 0, CLB200_ESTATE, "clXEngine: set_gather first");
+    DeviceGuard g(x->device);
+    // d_in: this rank's channel slab only, [t][station][shard channels][pol] (what work() uploads per rank)
+    return xe_launch(x, d_in, x->T, x->F, 0, nullptr, nullptr, 0, (cudaStream_t)stream, true);
 }
 
 int clb200_xengine_work(clb200_handle h, const void *in, void *out_c32, int accumulate)

@@ -164,6 +164,14 @@ __device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg,
                 if (i0 + k * XE_THREADS < nit)
                     of[i0 + k * XE_THREADS] = make_float2((float)v[k].x * scale, (float)v[k].y * scale);
         }
+        // fused all-gather: the same block goes into every rank's full matrix (peer-mapped over NVLink)
+        for (int g = 0; g < p.ngather; g++) {
+            float2 *dst = p.gather[g] + p.gather_off + (long)f0 * npp;
+#pragma unroll
+            for (int k = 0; k < UN; k++)
+                if (i0 + k * XE_THREADS < nit)
+                    dst[i0 + k * XE_THREADS] = make_float2((float)v[k].x * scale, (float)v[k].y * scale);
+        }
     }
 }
 

@@ -215,6 +215,26 @@ CLB200_API int clb200_xengine_launch_device_i32(clb200_handle h, const void *d_i
  * [chan_first, chan_first+chan_count) of an integration whose host layout has
  * total_channels per station; work() gathers only that slab (cudaMemcpy2D).      */
 CLB200_API int clb200_xengine_set_shard(clb200_handle h, int total_channels, int chan_first);
+/* Fused all-gather over peer memory (NVLink / NVSwitch), one process per GPU: every rank registers the
+ * full visibility matrix of EVERY rank (its own + the peers', opened with clb200_ipc_open); the
+ * correlation kernel's epilogue then writes this rank's channel slab straight into all of them
+ * (c32[total_channels][baselines][pol^2] at channel offset chan_first), so no collective follows the
+ * kernel.  The matrices are complete once every rank's stream has drained (a barrier of the caller's).
+ * Needs clb200_xengine_set_shard first and 16 B aligned input rows (the TMA kernel).               */
+#define CLB200_XENGINE_MAX_GATHER 8
+CLB200_API int clb200_xengine_set_gather(clb200_handle h, int nranks, void *const *full_out_c32);
+/* d_in: this rank's channel slab only, [t][station][shard channels][pol]                            */
+CLB200_API int clb200_xengine_launch_device_gather(clb200_handle h, const void *d_in, void *stream);
+
+/* ------------------------------------------------- device memory for peers -- */
+/* cudaMalloc'ed buffers whose interprocess handle (64 opaque bytes) other ranks of the same box can
+ * open; peer access is enabled on open.  Only the gather above needs them.                          */
+CLB200_API int clb200_mem_alloc(int device, size_t bytes, void **dptr);
+CLB200_API int clb200_mem_free(int device, void *dptr);
+CLB200_API int clb200_mem_copy_to_host(int device, const void *dptr, void *host, size_t bytes);
+CLB200_API int clb200_ipc_export(int device, void *dptr, void *handle64);
+CLB200_API int clb200_ipc_open(int device, const void *handle64, void **dptr);
+CLB200_API int clb200_ipc_close(int device, void *dptr);
 
 /* ================================================================================
  * SURVEY 8(f) "next" rows: the blocks either side of the hot path.

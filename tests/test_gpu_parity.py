@@ -368,3 +368,42 @@ def test_xengine_baseline_config_properties():
     lo = half.work_i32(np.ascontiguousarray(b4[:T // 2]))
     hi = half.work_i32(np.ascontiguousarray(b4[T // 2:]))
     assert np.array_equal((lo + hi).reshape(got.shape), got)
+
+
+def test_xengine_fused_gather_writes_every_registered_matrix():
+    """clb200_xengine_set_gather / launch_device_gather (the multi-GPU all-gather fused into the epilogue):
+    on one GPU two 'ranks' own half of the channels each and store their slabs into BOTH full matrices
+    (cudaMalloc'ed through the ABI, as the peers' matrices would be after clb200_ipc_open)."""
+    import torch
+    lib = capi.load()
+    A, F, T = 32, 64, 256
+    nbl = A * (A + 1) // 2
+    buf = orc.rng_i8(T * A * F * 2, orc.SEED_X + 11)
+    want = orc.xengine_exact(buf, A, F, T, 1).astype(np.float64) / (127.0 * 127.0)
+    mats = []
+    for _ in range(2):
+        p = C.c_void_p()
+        capi.check(lib.clb200_mem_alloc(0, F * nbl * 8, C.byref(p)))
+        mats.append(p)
+    b4 = buf.reshape(T, A, F, 2)
+    sp = torch.cuda.current_stream().cuda_stream
+    keep = []
+    for r in range(2):
+        blk = _xe(capi.DTYPE_BYTE, 1, A, F // 2, T)
+        blk.set_shard(F, r * (F // 2))
+        blk.set_gather([m.value for m in mats])
+        slab = torch.from_numpy(np.ascontiguousarray(b4[:, :, r * (F // 2):(r + 1) * (F // 2), :])).cuda()
+        blk.launch_device_gather(slab.data_ptr(), sp)
+        keep.append((blk, slab))
+    torch.cuda.synchronize()
+    for m in mats:
+        got = np.zeros(F * nbl, np.complex64)
+        capi.check(lib.clb200_mem_copy_to_host(0, m, got.ctypes.data_as(C.c_void_p), got.nbytes))
+        assert np.max(np.abs(got.real - want[:, 0])) < 1e-3 and np.max(np.abs(got.imag - want[:, 1])) < 1e-3
+        capi.check(lib.clb200_mem_free(0, m))
+    h = C.create_string_buffer(64)
+    p = C.c_void_p()
+    capi.check(lib.clb200_mem_alloc(0, 4096, C.byref(p)))
+    capi.check(lib.clb200_ipc_export(0, p, h))                 # a 64-byte handle another process could open
+    assert any(h.raw)
+    capi.check(lib.clb200_mem_free(0, p))
