@@ -114,6 +114,9 @@ class ClockSampler:
                 time.sleep(0.001)
         self.thr = threading.Thread(target=rd, daemon=True)
         self.thr.start()
+        t_end = time.perf_counter() + 2.0                 # NVML start-up can outlast the whole default run
+        while not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.001)
 
     def mark(self, which):
         if which == 0:
@@ -253,7 +256,7 @@ def secondary_blocks(torch, blocks, capi, dev, stream_ptr, hbm_peak):
         def f():
             blk.launch_device(bufs[it[0] % 4].data_ptr(), vis.data_ptr(), False, stream_ptr)
             it[0] += 1
-        t = timeit(f, 8)
+        t = timeit(f, 32)
         bytes_ = nb + vis.numel() * 4
         out["clXEngine_32st_1024ch_int1024"] = {
             "Msamples_s": A * F * T / t / 1e6, "us_per_integration": t * 1e6, "GBps": bytes_ / t / 1e9,
