@@ -255,13 +255,17 @@ const FiltVariant *pick_filt(int ntaps)
 {
     static const FiltVariant v10 = make_filt<10, 32, 12>();   // 1024 = 32^2: one warp per block, 1 exchange per FFT
                                                               // (12 CTAs/SM, 170 regs: 3.15 TB/s vs 2.76 for 4096 at 256 taps)
+    static const FiltVariant v10b = make_filt<10, 32, 16>();  // same, capped at 128 registers (A/B: CLB200_FILT_MINB=16)
     static const FiltVariant v12 = make_filt<12, 16, 2>();    // 4096 = 16^3 (register hand-over)
     static const FiltVariant v14 = make_filt<14, 16, 1>();    // 16384 = 16^3 * 4
     const char *e = getenv("CLB200_FILT_NF");                 // tuning: force the block size
     const int force = e ? atoi(e) : 0;
     if (force == 1024 && ntaps <= 1024) return &v10;
     if (force == 4096 && ntaps <= 4096) return &v12;
-    if (ntaps <= 513 && force == 0) return &v10;
+    if (ntaps <= 513 && force == 0) {
+        const char *mb = getenv("CLB200_FILT_MINB");
+        return (mb && atoi(mb) == 16) ? &v10b : &v10;
+    }
     if (ntaps <= 2049) return &v12;
     if (ntaps <= 8193) return &v14;
     return nullptr;
