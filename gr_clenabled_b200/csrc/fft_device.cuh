@@ -116,6 +116,19 @@ __device__ __forceinline__ float2 csub(float2 a, float2 c)
 #endif
 }
 
+// acc + (t, t) * v as one packed fma (FFMA2): tt must hold the same real factor in both halves
+__device__ __forceinline__ float2 cfma_real(float2 tt, float2 v, float2 acc)
+{
+#if CLB_F32X2
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&tt)),
+        "l"(*reinterpret_cast<unsigned long long *>(&v)), "l"(*reinterpret_cast<unsigned long long *>(&acc)));
+    return *reinterpret_cast<float2 *>(&r);
+#else
+    return make_float2(fmaf(tt.x, v.x, acc.x), fmaf(tt.y, v.y, acc.y));
+#endif
+}
+
 // In-register forward DFT of x[OFF .. OFF+R): radix-2 decimation in frequency.
 // Result is left in bit-reversed order: X[k] = x[OFF + bitrev(k)].
 template <int R, int OFF, int NREG>
