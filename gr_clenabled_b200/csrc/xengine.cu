@@ -530,6 +530,9 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     int fc = tc ? TC_FC : v->fc;
     if (tma_ok) {
         fc = ((x->F + 15) / 16 * 8 < sms) ? 8 : 16;      // 16 unless even 8 time slices per group leave SMs idle
+        // two polarisations: 8 channels are already 32 B runs, and enough 8-channel groups to fill the SMs need
+        // no time slicing, i.e. no exchange at all (measured 18.2 vs 20.7 us at 16 stations x 2 pols x 1024 channels)
+        if (x->npol == 2 && (x->F + 7) / 8 >= sms / 2 && (x->F + 7) / 8 <= sms) fc = 8;
         if (x->fc_override == 8 || x->fc_override == 16) fc = x->fc_override;
     }
     const int kt = tma_ok ? 512 / fc : XE_TT;           // time steps per stage
