@@ -78,3 +78,12 @@ def test_every_reference_grc_id_is_generated_with_its_parameter_ids(tmp_path):
         for ref in re.findall(r"\$\{\s*(\w+)", make):      # every ${param} used by make() is a declared parameter
             assert ref in have, (gid, ref)
         assert d["file_format"] == 1
+
+
+def test_import_clenabled_serves_every_class_the_grc_templates_name(tmp_path):
+    """GRC-generated flowgraphs do `import clenabled` and call `clenabled.<Class>(...)`"""
+    import clenabled
+    for f in gen_grc.main(str(tmp_path)):
+        make = yaml.safe_load(open(f))["templates"]["make"].strip()
+        cls = re.match(r"clenabled\.(\w+)\(", make).group(1)
+        assert getattr(clenabled, cls) is getattr(blocks, cls)
