@@ -21,6 +21,10 @@ using namespace clb200::fftdev;
 namespace {
 
 
+// experiment knob (CLB200_FFT_STAGGER_NS): the second wave of co-resident CTAs starts this much later, so the
+// load phase of one CTA of an SM meets the butterfly phase of the other
+__constant__ int c_fft_stagger_ns;
+
 // MODE bit 0: inverse (re/im swapped on load and store), bit 1: real input
 template <int LOGN, int EPT, int BATCH, int MINB, int MODE>
 __global__ void __launch_bounds__((1 << LOGN) / EPT * BATCH, MINB)
@@ -42,6 +46,7 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
     const int out_x = (shift && !inverse) ? (N >> 1) : 0;
 
     const long ntile = (nvec + BATCH - 1) / BATCH;
+    if (c_fft_stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep(c_fft_stagger_ns);
     for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const long v = tile * BATCH + tb;
         const bool active = v < nvec;
@@ -533,6 +538,11 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
         return fail(CLB200_ECUDA);
     }
     f->resident = occ;
+    {
+        const char *sg = getenv("CLB200_FFT_STAGGER_NS");
+        int ns = sg ? atoi(sg) : 0;
+        cudaMemcpyToSymbol(c_fft_stagger_ns, &ns, sizeof(int));
+    }
     // opt-in: measured on B200 it is on par (32 elements/thread) or slower (16) than the
     // plain kernel at 8192 points -- two resident CTAs already overlap each other's loads
     const char *pfenv = getenv("CLB200_FFT_PREFETCH");
