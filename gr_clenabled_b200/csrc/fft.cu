@@ -21,11 +21,7 @@ using namespace clb200::fftdev;
 namespace {
 
 
-// experiment knob (CLB200_FFT_STAGGER_NS): the second wave of co-resident CTAs starts this much later, so the
-// load phase of one CTA of an SM meets the butterfly phase of the other
-__constant__ int c_fft_stagger_ns;
-
-// MODE bit 0: inverse (re/im swapped on load and store), bit 1: real input
+// MODE bit 0: inverse (re/im swapped on load and store), bit 1: real input, bit 2: pass-1 twiddles in shared memory
 template <int LOGN, int EPT, int BATCH, int MINB, int MODE>
 __global__ void __launch_bounds__((1 << LOGN) / EPT * BATCH, MINB)
 k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
@@ -33,8 +29,16 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
 {
     using P = Plan<LOGN, EPT>;
     constexpr int N = P::N, T = P::T;
-    constexpr bool inverse = MODE & 1, real_in = MODE & 2;
+    constexpr bool inverse = MODE & 1, real_in = MODE & 2, tw1_smem = (MODE & 4) && P::npass() > 1;
     extern __shared__ __align__(16) float2 smem[];
+    const float2 *tw1s = nullptr;
+    if constexpr (tw1_smem) {
+        constexpr int N1 = P::tw_offset(2 < P::npass() ? 2 : P::npass()) - P::tw_offset(1);
+        float2 *dst = smem + BATCH * P::SMEM_F2;
+        for (int i = threadIdx.x; i < N1; i += T * BATCH) dst[i] = __ldg(tw + P::tw_offset(1) + i);
+        __syncthreads();
+        tw1s = dst;
+    }
 
     const int tb = (BATCH == 1) ? 0 : threadIdx.x / T;     // transform within the CTA
     const int lt = (BATCH == 1) ? threadIdx.x : threadIdx.x % T;
@@ -46,7 +50,6 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
     const int out_x = (shift && !inverse) ? (N >> 1) : 0;
 
     const long ntile = (nvec + BATCH - 1) / BATCH;
-    if (c_fft_stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep(c_fft_stagger_ns);
     for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const long v = tile * BATCH + tb;
         const bool active = v < nvec;
@@ -78,7 +81,7 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
             for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
         }
 
-        fft_core<P, EPT>(x, buf, lt, tw);
+        fft_core<P, EPT>(x, buf, lt, tw, NoHook{}, tw1s);
 
         if (active) {
             float2 *dst_up = out + v * N + lt + out_x, *dst_dn = out + v * N + lt - out_x;
@@ -213,6 +216,8 @@ struct FftVariant {
     void (*kernel[3])(const float2 *, float2 *, long, const float2 *, const float *, int);
     void (*kernel_pf[2])(const float2 *, float2 *, long, const float2 *, const float *, int);   // or null
     void (*kernel_xc)(const float2 *, const float2 *, float *, long, const float2 *);           // FFT correlator
+    void (*kernel_s[2])(const float2 *, float2 *, long, const float2 *, const float *, int);    // pass-1 twiddles in smem
+    int tw1_bytes;
 };
 
 template <int LOGN, int EPT>
@@ -248,6 +253,9 @@ FftVariant make_variant()
     v.kernel[2] = &k_fft<LOGN, EPT, BATCH, MINB, 2>;     // forward, real input
     v.kernel_pf[0] = v.kernel_pf[1] = nullptr;
     v.kernel_xc = &k_xcfft<LOGN, EPT, BATCH, MINB>;
+    v.kernel_s[0] = &k_fft<LOGN, EPT, BATCH, MINB, 4>;
+    v.kernel_s[1] = &k_fft<LOGN, EPT, BATCH, MINB, 5>;
+    v.tw1_bytes = P::npass() > 1 ? (P::tw_offset(2 < P::npass() ? 2 : P::npass()) - P::tw_offset(1)) * (int)sizeof(float2) : 0;
     if constexpr (BATCH == 1 && LOGN >= 12) {
         v.kernel_pf[0] = &k_fft_pf<LOGN, EPT, MINB, 0>;
         v.kernel_pf[1] = &k_fft_pf<LOGN, EPT, MINB, 1>;
@@ -289,6 +297,7 @@ struct Fft : clb200_block {
     Buf d_tw, d_win;
     int resident = 1;     // CTAs per SM the launch is sized for
     bool use_pf = false;  // bulk-copy prefetching kernel available and enabled
+    bool use_tw1s = false; // pass-1 twiddles in shared memory (k_fft<.., MODE|4>)
     ~Fft() override
     {
         DeviceGuard g(device);
@@ -307,6 +316,10 @@ int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st
     const bool pf = f->use_pf && (((uintptr_t)d_in & 15) == 0);
     if (pf)
         v->kernel_pf[f->mode]<<<std::min<long>(grid, nvec), v->threads, v->smem_bytes + 16, st>>>(
+            (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
+            f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
+    else if (f->use_tw1s)
+        v->kernel_s[f->mode]<<<grid, v->threads, v->smem_bytes + v->tw1_bytes, st>>>(
             (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
             f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
     else
@@ -539,9 +552,18 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
     }
     f->resident = occ;
     {
-        const char *sg = getenv("CLB200_FFT_STAGGER_NS");
-        int ns = sg ? atoi(sg) : 0;
-        cudaMemcpyToSymbol(c_fft_stagger_ns, &ns, sizeof(int));
+        // pass-1 twiddle table in shared memory (complex modes, tables up to 8 KiB) when it keeps the occupancy
+        const char *ts = getenv("CLB200_FFT_TW1S");
+        const int want = ts ? atoi(ts) : 0;
+        if (want && f->mode < 2 && f->var->tw1_bytes > 0 && f->var->tw1_bytes <= 8192) {
+            const void *k = (const void *)f->var->kernel_s[f->mode];
+            int occ2 = 0;
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, f->var->smem_bytes + f->var->tw1_bytes) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k, f->var->threads, f->var->smem_bytes + f->var->tw1_bytes) == cudaSuccess &&
+                occ2 >= occ)
+                f->use_tw1s = true;
+            cudaGetLastError();
+        }
     }
     // opt-in: measured on B200 it is on par (32 elements/thread) or slower (16) than the
     // plain kernel at 8192 points -- two resident CTAs already overlap each other's loads

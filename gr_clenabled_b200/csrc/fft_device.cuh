@@ -267,9 +267,13 @@ struct NoHook {
 // after_last_load() runs once, right after the last pass has read its inputs out of
 // shared memory (the buffer is dead from then on for this transform) -- the
 // prefetching kernel uses it to start the bulk copy of the next vector.
+// tw1s (optional): a shared-memory copy of the pass-1 twiddle table (P::tw_offset(1) .. tw_offset(2)); its
+// entries are the same for every transform a thread runs, and reading them with LDS keeps them out of the
+// global-load queue (the 8192-point kernel stalls on lg_throttle: 59 twiddle LDGs per 32 data LDGs).
 template <class P, int EPT, class Hook = NoHook>
 __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
-                                         const float2 *__restrict__ tw, Hook after_last_load = Hook{})
+                                         const float2 *__restrict__ tw, Hook after_last_load = Hook{},
+                                         const float2 *tw1s = nullptr)
 {
     constexpr int N = P::N, T = P::T, NPASS = P::npass();
     // P::pad(a + c) == P::pad(a) + P::pad(c) whenever c is a multiple of the granularity, so nearly every
@@ -297,9 +301,15 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
             constexpr int u = decltype(u_)::value;
             if constexpr (!first) {
                 const int k = (lt + u * T) & (NS - 1);
-                const float2 *t = tw + P::tw_offset(p) + k;
+                if (p == 1 && tw1s != nullptr) {
+                    const float2 *t = tw1s + k;
 #pragma unroll
-                for (int r = 1; r < R; r++) x[u * R + r] = cmul(x[u * R + r], __ldg(t + (r - 1) * NS));
+                    for (int r = 1; r < R; r++) x[u * R + r] = cmul(x[u * R + r], t[(r - 1) * NS]);
+                } else {
+                    const float2 *t = tw + P::tw_offset(p) + k;
+#pragma unroll
+                    for (int r = 1; r < R; r++) x[u * R + r] = cmul(x[u * R + r], __ldg(t + (r - 1) * NS));
+                }
             }
             dft_dif<R, u * R>(x);
         });
