@@ -11,6 +11,9 @@
 // HBM traffic: 8 B read + 8 B written per sample = 16 B/sample (algorithmic
 // minimum); the transform itself lives in shared memory/registers.
 #include "common.cuh"
+#ifndef CLB_TW_DERIVE
+#define CLB_TW_DERIVE 2      // see fft_device.cuh
+#endif
 #include "fft_device.cuh"
 #include <cmath>
 #include <cstdlib>

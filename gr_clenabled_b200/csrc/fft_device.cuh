@@ -93,6 +93,16 @@ __device__ __forceinline__ float2 mul_w32(float2 a)
 #ifndef CLB_F32X2
 #define CLB_F32X2 1
 #endif
+// Twiddle loads traded for arithmetic (the FFT kernels are co-limited by L1 wavefronts and load-queue
+// stalls while the FP32 pipe is under 40 % busy):
+//   1: last pass, several sub-blocks per thread -- one table load per r, the other sub-blocks rotate it by a
+//      compile-time W_32 power (8192 points: 59 -> 38 twiddle loads per thread, 4.92 -> 5.17 TB/s);
+//   2: additionally only r = 1, 2, 4, ... are loaded and the other W^(r*k) are products of those (one to four
+//      extra roundings, error unchanged at 2e-7): 4096 points 5.14 -> 5.76 TB/s, 8192 +0.4 %.  Used by fft.cu;
+//      the one-warp FFT filter is slower with it (3.66 -> 3.50 TB/s) and stays at 1.
+#ifndef CLB_TW_DERIVE
+#define CLB_TW_DERIVE 1
+#endif
 __device__ __forceinline__ float2 cadd(float2 a, float2 c)
 {
 #if CLB_F32X2
@@ -297,14 +307,44 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
             else after_last_load();
         }
 
+#if CLB_TW_DERIVE
+        // last pass with several sub-blocks per thread: k = lt + u*T, so W^(r*k) = W^(r*lt) * W_32^(r*u*32/EPT):
+        // one table load per r, the sub-blocks u > 0 rotate it by a compile-time constant
+        constexpr bool derive = !first && last && NB > 1 && R >= 4 && NS * R == N;   // (radix 2: three loads saved do not pay)
+        if constexpr (derive) {
+            const float2 *t = tw + P::tw_offset(p) + lt;
+            float2 wp[R] = {};
+            static_for<1, R>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                if constexpr (CLB_TW_DERIVE >= 2 && (r & (r - 1)) != 0) wp[r] = cmul(wp[r & (r - 1)], wp[r & -r]);
+                else wp[r] = __ldg(t + (r - 1) * NS);
+                static_for<0, NB>([&](auto u_) {
+                    constexpr int u = decltype(u_)::value;
+                    x[u * R + r] = cmul(x[u * R + r], mul_w32<(r * u * (32 / EPT)) % 32>(wp[r]));
+                });
+            });
+        }
+#else
+        constexpr bool derive = false;
+#endif
         static_for<0, NB>([&](auto u_) {
             constexpr int u = decltype(u_)::value;
-            if constexpr (!first) {
+            if constexpr (!first && !derive) {
                 const int k = (lt + u * T) & (NS - 1);
                 if (p == 1 && tw1s != nullptr) {
                     const float2 *t = tw1s + k;
 #pragma unroll
                     for (int r = 1; r < R; r++) x[u * R + r] = cmul(x[u * R + r], t[(r - 1) * NS]);
+                } else if constexpr (CLB_TW_DERIVE >= 2 && R >= 8) {
+                    // W^(r*k) for r = 1, 2, 4, ... from the table, the other r as products of those
+                    const float2 *t = tw + P::tw_offset(p) + k;
+                    float2 wp[R] = {};
+                    static_for<1, R>([&](auto r_) {
+                        constexpr int r = decltype(r_)::value;
+                        if constexpr ((r & (r - 1)) != 0) wp[r] = cmul(wp[r & (r - 1)], wp[r & -r]);
+                        else wp[r] = __ldg(t + (r - 1) * NS);
+                        x[u * R + r] = cmul(x[u * R + r], wp[r]);
+                    });
                 } else {
                     const float2 *t = tw + P::tw_offset(p) + k;
 #pragma unroll
