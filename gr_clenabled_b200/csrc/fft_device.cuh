@@ -316,7 +316,7 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
             float2 wp[R] = {};
             static_for<1, R>([&](auto r_) {
                 constexpr int r = decltype(r_)::value;
-                if constexpr (CLB_TW_DERIVE >= 2 && (r & (r - 1)) != 0) wp[r] = cmul(wp[r & (r - 1)], wp[r & -r]);
+                if constexpr (CLB_TW_DERIVE >= 2 && N >= 512 && (r & (r - 1)) != 0) wp[r] = cmul(wp[r & (r - 1)], wp[r & -r]);
                 else wp[r] = __ldg(t + (r - 1) * NS);
                 static_for<0, NB>([&](auto u_) {
                     constexpr int u = decltype(u_)::value;
@@ -335,7 +335,7 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
                     const float2 *t = tw1s + k;
 #pragma unroll
                     for (int r = 1; r < R; r++) x[u * R + r] = cmul(x[u * R + r], t[(r - 1) * NS]);
-                } else if constexpr (CLB_TW_DERIVE >= 2 && R >= 8) {
+                } else if constexpr (CLB_TW_DERIVE >= 2 && R >= 8 && N >= 512) {       // (64 / 256 points: -1.5 % with it)
                     // W^(r*k) for r = 1, 2, 4, ... from the table, the other r as products of those
                     const float2 *t = tw + P::tw_offset(p) + k;
                     float2 wp[R] = {};
