@@ -51,6 +51,9 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
     // so the half swap is a choice between two base pointers per compile-time c.
     const int in_x = (shift && inverse) ? (N >> 1) : 0;
     const int out_x = (shift && !inverse) ? (N >> 1) : 0;
+    // 2-, 4- and 8-point transforms (one thread each, one pass): vector I/O when both pointers are 16 B aligned
+    constexpr bool one_thread = T == 1 && !real_in && N >= 2 && P::npass() == 1 && EPT == N;
+    const bool vec_io = one_thread && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
 
     const long ntile = (nvec + BATCH - 1) / BATCH;
     for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
@@ -62,6 +65,24 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
             const float2 *src_up = in + v * N + lt + in_x, *src_dn = in + v * N + lt - in_x;
             const float *srf_up = reinterpret_cast<const float *>(in) + v * N + lt + in_x;
             const float *srf_dn = reinterpret_cast<const float *>(in) + v * N + lt - in_x;
+            if (vec_io) {
+                // one thread per transform: its N samples are contiguous -- 128-bit loads (two samples), through L1
+                // so that the sectors a warp's strided requests share are fetched once
+                if constexpr (one_thread && N == 2) {         // the half swap exchanges the two samples
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(in + v * N));
+                    const float2 s0 = in_x ? make_float2(a.z, a.w) : make_float2(a.x, a.y);
+                    const float2 s1 = in_x ? make_float2(a.x, a.y) : make_float2(a.z, a.w);
+                    x[0] = inverse ? make_float2(s0.y, s0.x) : s0;
+                    x[1] = inverse ? make_float2(s1.y, s1.x) : s1;
+                } else if constexpr (one_thread) {
+                    static_for<0, EPT / 2>([&](auto q_) {
+                        constexpr int c = 2 * decltype(q_)::value;
+                        const float4 a = __ldg(reinterpret_cast<const float4 *>(((c & (N >> 1)) ? src_dn : src_up) + c));
+                        x[c] = inverse ? make_float2(a.y, a.x) : make_float2(a.x, a.y);
+                        x[c + 1] = inverse ? make_float2(a.w, a.z) : make_float2(a.z, a.w);
+                    });
+                }
+            } else
             static_for<0, EPT>([&](auto e_) {
                 constexpr int e = decltype(e_)::value;
                 constexpr int c = in_index<P, EPT>(0, e);
@@ -88,6 +109,21 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
 
         if (active) {
             float2 *dst_up = out + v * N + lt + out_x, *dst_dn = out + v * N + lt - out_x;
+            if (vec_io) {
+                if constexpr (one_thread && N == 2) {
+                    const float2 a = out_x ? x[1] : x[0], b = out_x ? x[0] : x[1];
+                    const float4 o = inverse ? make_float4(a.y, a.x, b.y, b.x) : make_float4(a.x, a.y, b.x, b.y);
+                    __stcs(reinterpret_cast<float4 *>(out + v * N), o);
+                } else if constexpr (one_thread) {
+                    constexpr int LN = ilog2(N);                 // single pass: X[k] = x[bitrev(k)]
+                    static_for<0, EPT / 2>([&](auto q_) {
+                        constexpr int c = 2 * decltype(q_)::value;
+                        const float2 a = x[bitrev(c, LN)], b = x[bitrev(c + 1, LN)];
+                        const float4 o = inverse ? make_float4(a.y, a.x, b.y, b.x) : make_float4(a.x, a.y, b.x, b.y);
+                        __stcs(reinterpret_cast<float4 *>(((c & (N >> 1)) ? dst_dn : dst_up) + c), o);
+                    });
+                }
+            } else
             for_each_output_c<P, EPT>(x, [&](auto c_, float2 a) {
                 constexpr int c = decltype(c_)::value;
                 if (inverse) a = make_float2(a.y, a.x);

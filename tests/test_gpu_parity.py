@@ -112,7 +112,7 @@ def test_fft_forward_all_sizes(N):
     assert rel_err(got, want) < 2e-6
 
 
-@pytest.mark.parametrize("N", [8, 64, 2048, 8192])
+@pytest.mark.parametrize("N", [2, 4, 8, 64, 2048, 8192])
 def test_fft_backward_window_shift(N, golden):
     x = orc.rng_c32(N * 4, orc.SEED_F + 1)
     w = orc.window_blackman(N)
@@ -121,6 +121,29 @@ def test_fft_backward_window_shift(N, golden):
             for shift in (False, True):
                 blk = blocks.clFFT(N, direction, [] if win is None else win, capi.DTYPE_COMPLEX, *GPU, 0, 1, shift)
                 assert rel_err(blk.work(x), orc.fft(x, N, direction, win, shift)) < TOL, (direction, win is None, shift)
+
+
+@pytest.mark.parametrize("N", [2, 4, 8])
+def test_fft_small_sizes_unaligned_device_pointers(N):
+    """4- and 8-point transforms use 128-bit loads/stores when the pointers allow it; 8-byte-aligned device
+    pointers must take the scalar path and give the same bits"""
+    import torch
+    nvec = 1000
+    x = orc.rng_c32(N * nvec, orc.SEED_F + 9)
+    sp = torch.cuda.current_stream().cuda_stream
+    for shift in (False, True):
+        blk = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU, 0, 1, shift)
+        want = orc.fft(x, N, capi.FFT_FORWARD, None, shift)
+        outs = []
+        for off in (0, 1):                                   # float2 units
+            d_in = torch.zeros(2 * (N * nvec + 2), dtype=torch.float32, device="cuda")
+            d_out = torch.zeros_like(d_in)
+            d_in[2 * off:2 * off + 2 * N * nvec] = torch.from_numpy(x.view(np.float32)).cuda()
+            blk.launch_device(d_in.data_ptr() + 8 * off, d_out.data_ptr() + 8 * off, nvec, sp)
+            torch.cuda.synchronize()
+            outs.append(d_out[2 * off:2 * off + 2 * N * nvec].cpu().numpy().view(np.complex64))
+        assert np.array_equal(outs[0], outs[1])
+        assert rel_err(outs[0], want) < TOL
 
 
 def test_fft_tone_known_answer(golden):
