@@ -311,7 +311,7 @@ const FftVariant *pick_variant(int logn)
         make_variant<4, 4, 8, 24>(),    make_variant<5, 8, 8, 24>(),   make_variant<6, 8, 4, 24>(),
         make_variant<7, 8, 2, 24>(),    make_variant<8, 16, 16, 2>(),  make_variant<9, 8, 4, 4>(),
         make_variant<10, 16, 4, 2>(),   make_variant<11, 16, 2, 2>(),  make_variant<12, 16, 1, 2>(),
-        make_variant<13, 32, 1, 2>(),   make_variant<14, 16, 1, 1>(),
+        make_variant<13, 32, 1, 2>(),   make_variant<14, 32, 1, 1>(),
     };
     static const FftVariant alt[] = {
         make_variant<13, 16, 1, 2>(),   // CLB200_FFT_VARIANT=1
