@@ -280,7 +280,8 @@ struct NoHook {
 // tw1s (optional): a shared-memory copy of the pass-1 twiddle table (P::tw_offset(1) .. tw_offset(2)); its
 // entries are the same for every transform a thread runs, and reading them with LDS keeps them out of the
 // global-load queue (the 8192-point kernel stalls on lg_throttle: 59 twiddle LDGs per 32 data LDGs).
-template <class P, int EPT, class Hook = NoHook>
+// TWD: twiddle derivation mode (see CLB_TW_DERIVE)
+template <class P, int EPT, class Hook = NoHook, int TWD = CLB_TW_DERIVE>
 __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
                                          const float2 *__restrict__ tw, Hook after_last_load = Hook{},
                                          const float2 *tw1s = nullptr)
@@ -307,16 +308,15 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
             else after_last_load();
         }
 
-#if CLB_TW_DERIVE
         // last pass with several sub-blocks per thread: k = lt + u*T, so W^(r*k) = W^(r*lt) * W_32^(r*u*32/EPT):
         // one table load per r, the sub-blocks u > 0 rotate it by a compile-time constant
-        constexpr bool derive = !first && last && NB > 1 && R >= 4 && NS * R == N;   // (radix 2: three loads saved do not pay)
+        constexpr bool derive = TWD >= 1 && !first && last && NB > 1 && R >= 4 && NS * R == N;   // (radix 2: three loads saved do not pay)
         if constexpr (derive) {
             const float2 *t = tw + P::tw_offset(p) + lt;
             float2 wp[R] = {};
             static_for<1, R>([&](auto r_) {
                 constexpr int r = decltype(r_)::value;
-                if constexpr (CLB_TW_DERIVE >= 2 && N >= 512 && (r & (r - 1)) != 0) wp[r] = cmul(wp[r & (r - 1)], wp[r & -r]);
+                if constexpr (TWD >= 2 && N >= 512 && (r & (r - 1)) != 0) wp[r] = cmul(wp[r & (r - 1)], wp[r & -r]);
                 else wp[r] = __ldg(t + (r - 1) * NS);
                 static_for<0, NB>([&](auto u_) {
                     constexpr int u = decltype(u_)::value;
@@ -324,9 +324,6 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
                 });
             });
         }
-#else
-        constexpr bool derive = false;
-#endif
         static_for<0, NB>([&](auto u_) {
             constexpr int u = decltype(u_)::value;
             if constexpr (!first && !derive) {
@@ -335,7 +332,7 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
                     const float2 *t = tw1s + k;
 #pragma unroll
                     for (int r = 1; r < R; r++) x[u * R + r] = cmul(x[u * R + r], t[(r - 1) * NS]);
-                } else if constexpr (CLB_TW_DERIVE >= 2 && R >= 8 && N >= 512) {       // (64 / 256 points: -1.5 % with it)
+                } else if constexpr (TWD >= 2 && R >= 8 && N >= 512) {       // (64 / 256 points: -1.5 % with it)
                     // W^(r*k) for r = 1, 2, 4, ... from the table, the other r as products of those
                     const float2 *t = tw + P::tw_offset(p) + k;
                     float2 wp[R] = {};

@@ -50,6 +50,9 @@ k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n
     constexpr int N = P::N, NPASS = P::npass();
     constexpr int R0 = P::radix(0), RL = P::radix(NPASS - 1), NSL = P::ns(NPASS - 1);
     constexpr int LRL = ilog2(RL);
+    // twiddles multiplied up from the power-of-two table entries for the multi-warp block sizes; the one-warp
+    // 1024-point blocks are issue-latency bound and lose 4 % with it
+    constexpr int TWD = P::T > 32 ? 2 : 1;
     extern __shared__ __align__(16) float2 smem[];
     const int lt = threadIdx.x;
     const int km1 = K - 1;
@@ -73,7 +76,7 @@ k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n
                 x[e] = stream_at(hist, in, base + in_index<P, EPT>(lt, e), km1, n_in);
         }
 
-        fft_core<P, EPT>(x, smem, lt, tw);
+        fft_core<P, EPT, NoHook, TWD>(x, smem, lt, tw);
 
         // spectrum * H, then re-order into first-pass order with re/im swapped (inverse)
         float2 y[EPT];
@@ -100,7 +103,7 @@ k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n
             for (int e = 0; e < EPT; e++) y[e] = smem[P::pad(in_index<P, EPT>(lt, e))];
         }
 
-        fft_core<P, EPT>(y, smem, lt, tw);
+        fft_core<P, EPT, NoHook, TWD>(y, smem, lt, tw);
 
         if (D == 1 && base + L <= n_in) {
             // every valid output of the block exists: one predicate per element
