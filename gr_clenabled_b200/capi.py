@@ -16,7 +16,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "clenabled_b200.h"
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
 
-DTYPE_COMPLEX, DTYPE_FLOAT, DTYPE_INT, DTYPE_BYTE, DTYPE_PACKEDXY = 1, 2, 3, 4, 6
+# include/clenabled/GRCLBase.h:57-62
+DTYPE_COMPLEX, DTYPE_FLOAT, DTYPE_INT, DTYPE_SHORT, DTYPE_BYTE, DTYPE_PACKEDXY = 1, 2, 3, 4, 5, 6
 OP_MULTIPLY, OP_ADD, OP_SUBTRACT, OP_COMPLEX_CONJ, OP_MULTIPLY_CONJ = 1, 2, 3, 4, 5
 OP_EMPTY, OP_EMPTY_W_COPY = 255, 254
 FFT_FORWARD, FFT_BACKWARD = -1, 1

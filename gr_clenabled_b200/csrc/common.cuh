@@ -164,6 +164,22 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
         }
     }
 
+    // any early (error) return below leaves nothing in flight and no slot marked busy: a later call
+    // must never drain a stale slot into a different caller buffer
+    struct SlotGuard {
+        clb200_block *b;
+        bool armed = true;
+        ~SlotGuard()
+        {
+            if (!armed) return;
+            for (int i = 0; i < NSLOT; i++) {
+                if (b->slot[i].stream) cudaStreamSynchronize(b->slot[i].stream);
+                b->slot[i].busy = false;
+            }
+            cudaGetLastError();
+        }
+    } guard{b};
+
     auto drain = [&](Slot &s) -> int {
         if (!s.busy) return CLB200_OK;
         CLB_CUDA(cudaEventSynchronize(s.done));
@@ -222,6 +238,7 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
     }
     // drain in issue order
     for (long i = 0; i < NSLOT; i++) CLB_TRY(drain(b->slot[(c + i) % NSLOT]));
+    guard.armed = false;
     if (total_out) *total_out = out_pos;
     return CLB200_OK;
 }

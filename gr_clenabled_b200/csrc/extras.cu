@@ -285,7 +285,8 @@ int cf_configure(CFilter *f, const std::vector<float2> &taps)
     }
     const size_t smem = sizeof(float2) * ((size_t)2 * K + CF_TILE);
     CLB_CHECK(smem <= 200 * 1024, CLB200_EINVAL, "clComplexFilter: %d taps do not fit shared memory", K);
-    CLB_CUDA(cudaFuncSetAttribute((const void *)k_cfir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // per-function limit, shared by all handles: the cap, not this filter's size
+    CLB_CUDA(cudaFuncSetAttribute((const void *)k_cfir, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     f->hist_pending = false;
     return CLB200_OK;
 }
@@ -357,11 +358,16 @@ struct QuadDemod : clb200_block {
     float gain = 1.0f;
     Buf d_prev[2];
     int cur = 0;
+    // consecutive launches may sit on different streams (the chunks of one work() call rotate over the
+    // handle's slot streams): the kernel that reads d_prev waits for the k_qd_keep that wrote it
+    cudaEvent_t prev_ready = nullptr;
+    bool prev_pending = false;
     ~QuadDemod() override
     {
         DeviceGuard g(device);
         d_prev[0].release();
         d_prev[1].release();
+        if (prev_ready) cudaEventDestroy(prev_ready);
     }
 };
 
@@ -369,10 +375,14 @@ int qd_launch(QuadDemod *q, const float2 *d_in, float *d_out, long n, cudaStream
 {
     if (n <= 0) return CLB200_OK;
     const int sms = device_sm_count(q->device);
+    if (q->prev_pending) CLB_CUDA(cudaStreamWaitEvent(st, q->prev_ready, 0));
     k_quaddemod<<<grid_for((n + 255) / 256, sms, 8), 256, 0, st>>>((const float2 *)q->d_prev[q->cur].p, d_in, d_out, n,
                                                                    q->gain, q->gain != 1.0f);
     k_qd_keep<<<1, 32, 0, st>>>(d_in, n, (float2 *)q->d_prev[q->cur ^ 1].p);
     CLB_CUDA(cudaGetLastError());
+    if (!q->prev_ready) CLB_CUDA(cudaEventCreateWithFlags(&q->prev_ready, cudaEventDisableTiming));
+    CLB_CUDA(cudaEventRecord(q->prev_ready, st));
+    q->prev_pending = true;
     q->cur ^= 1;
     q->n_launch += 2;
     return CLB200_OK;

@@ -545,7 +545,8 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
     f->logn = ilog2(fft_size);
     f->dir = dir;
     f->dtype = dtype;
-    f->shift = shift ? 1 : 0;
+    // the reference shifts complex data only: a real-input spectrum is left unshifted (lib/clFFT_impl.cc:594)
+    f->shift = (shift && dtype == CLB200_DTYPE_COMPLEX) ? 1 : 0;
     f->mode = dtype == CLB200_DTYPE_FLOAT ? 2 : (dir > 0 ? 1 : 0);
     f->var = pick_variant(f->logn);
     auto fail = [&](int rc) {

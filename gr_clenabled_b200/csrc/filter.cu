@@ -332,8 +332,10 @@ int filter_configure(Filter *f, const std::vector<float> &taps)
         CLB_CUDA(cudaMemcpy(f->d_rtaps.p, rt.data(), sizeof(float) * f->k8, cudaMemcpyHostToDevice));
         size_t smem = (size_t)f->k8 * 4 + sizeof(float2) * fir_pad(FIR_TILE + f->k8 + 8);
         CLB_CHECK(smem <= 200 * 1024, CLB200_EINVAL, "clFilter: %d taps exceed the FIR kernel's shared memory", K);
-        CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_d1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(f->k8 * 4)));
+        // the limit is per-function state shared by every clFilter handle of the process: always the cap the
+        // kernels may need, never the size of the filter configured last
+        CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_d1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         // as many resident CTAs as fit (5 at 256 taps): one CTA's tile load and barriers hide behind the
         // others' FMA loops -- 32.2 (2 CTAs/SM) -> 38.0 Gsamples/s at 256 taps
         int occ = 0;

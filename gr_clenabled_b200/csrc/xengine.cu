@@ -734,7 +734,7 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
     CLB_CHECK(npol == 1 || npol == 2, CLB200_EINVAL, "clXEngine: polarization must be 1 or 2, got %d", npol);
     CLB_CHECK(data_type == CLB200_DTYPE_COMPLEX || data_type == CLB200_DTYPE_BYTE ||
                   data_type == CLB200_DTYPE_PACKEDXY,
-              CLB200_EINVAL, "clXEngine: data type %d is not complex(1), byte(4) or packed-XY(6)", data_type);
+              CLB200_EINVAL, "clXEngine: data type %d is not complex(1), byte(5) or packed-XY(6)", data_type);
     CLB_CHECK(num_channels >= 1 && integration >= 1, CLB200_EINVAL,
               "clXEngine: num_channels and integration must be positive");
     CLB_CHECK((long)num_inputs * num_channels * npol * 2 * 32 < (1L << 31), CLB200_EINVAL,

@@ -107,7 +107,7 @@ def simple(gid, label, cls, ins, outs, extra=None, args=""):
 
 NK = [par("n_val", "n", "float", 1), par("k_val", "k", "float", 0)]
 XE_TYPE = enum("type", "Input Type", ["complex", "ichar", "packed4"], ["Complex", "Byte (IChar)", "Packed 4-bit XY"],
-               option_attributes={"data_type": ["1", "4", "6"], "input_format": ["complex", "byte", "byte"]})
+               option_attributes={"data_type": ["1", "5", "6"], "input_format": ["complex", "byte", "byte"]})
 XC_TYPE = enum("type", "Input Type", ["complex", "float"],
                option_attributes={"data_type": ["1", "2"], "size": ["8", "4"]})
 BOOL = lambda pid, label: enum(pid, label, ["False", "True"], ["No", "Yes"])     # noqa: E731

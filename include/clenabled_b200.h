@@ -47,11 +47,13 @@ extern "C" {
 #define CLB200_ENOMEM   -3
 #define CLB200_ESTATE   -4   /* call not valid in the handle's current state */
 
-/* data types: include/clenabled/GRCLBase.h:57-62 */
+/* data types: include/clenabled/GRCLBase.h:57-62 (the numeric values of the reference: saved flowgraphs
+ * and reference-API callers pass them as plain ints) */
 #define CLB200_DTYPE_COMPLEX   1
 #define CLB200_DTYPE_FLOAT     2
 #define CLB200_DTYPE_INT       3
-#define CLB200_DTYPE_BYTE      4   /* clXEngine IChar: interleaved int8 re,im */
+#define CLB200_DTYPE_SHORT     4   /* reserved: no hot-path block takes int16 */
+#define CLB200_DTYPE_BYTE      5   /* clXEngine IChar: interleaved int8 re,im */
 #define CLB200_DTYPE_PACKEDXY  6   /* clXEngine packed 4-bit */
 
 /* operator codes: include/clenabled/clMathOpTypes.h:11-20 */
@@ -138,7 +140,8 @@ CLB200_API int clb200_magphase2c_work(clb200_handle h, const float *mag, const f
  * dtype COMPLEX: c32[fft_size] -> c32[fft_size] per item; dtype FLOAT (forward
  * only): f32[fft_size] -> full Hermitian c32[fft_size] spectrum (:556-565,608-630).
  * Unnormalised in both directions (:121-122).  shift: forward swaps the output
- * halves (:594-607), backward swaps the input halves (:548-553).
+ * halves (:594-607), backward swaps the input halves (:548-553); complex data only --
+ * with dtype FLOAT the flag is ignored like the reference does (:594).
  * fft_size: power of two, 2 .. 16384.                                             */
 CLB200_API int clb200_fft_create(int fft_size, int dir, const float *window, int window_len,
                                  int dtype, int device, int shift, clb200_handle *out);

@@ -167,6 +167,22 @@ def test_fft_real_input_and_streams():
         assert rel_err(oi, orc.fft(xi, N, -1)) < TOL
 
 
+@pytest.mark.parametrize("N", [2, 8, 64, 1024, 8192, 16384])
+def test_fft_real_input_sizes_window_and_ignored_shift(N, golden):
+    """dtype FLOAT: full Hermitian spectrum, window applied, and the shift flag ignored like the reference
+    (lib/clFFT_impl.cc:594 shifts complex data only)"""
+    nvec = 3
+    x = orc.rng_f32(N * nvec, orc.SEED_F + 4)
+    w = golden["win_blackman_8192"] if N == 8192 else orc.window_blackman(N)
+    for win in (None, w):
+        want = orc.fft_real(x, N, win)
+        ref = np.fft.fft((x.reshape(nvec, N) * (1.0 if win is None else win)).astype(np.float64), axis=1).reshape(-1)
+        assert rel_err(want, ref) < 2e-6
+        for shift in (False, True):
+            got = blocks.clFFT(N, capi.FFT_FORWARD, [] if win is None else win, capi.DTYPE_FLOAT, *GPU, 0, 1, shift).work(x)
+            assert rel_err(got, want) < TOL, (win is None, shift)
+
+
 def test_fft_full_size_properties():
     """BASELINE config 2 at scale: 4096 vectors of 8192 (256 MiB in) -- Parseval, linearity and
     forward->backward round trip, none of which needs the oracle to transform 32 Mi samples."""

@@ -226,6 +226,14 @@ def test_quadrature_demod_and_signal_source():
     got = np.concatenate([blk.work(x[:1]), blk.work(x[1:4097]), blk.work(x[4097:])])
     want = orc.quad_demod(np.concatenate([np.zeros(1, c64), x]), 2.5)
     assert np.max(np.abs(got - want)) < 1e-5
+    # a call longer than one 32 MiB staging chunk: consecutive chunks run on different slot streams and each
+    # needs the previous chunk's last sample (event-ordered in qd_launch)
+    xl = orc.rng_c32(9_000_001, 82)
+    blk = blocks.clQuadratureDemod(1.0, *GPU)
+    for rep in range(3):
+        got = blk.work(xl)
+        want = orc.quad_demod(np.concatenate([np.zeros(1, c64) if rep == 0 else xl[-1:], xl]), 1.0)
+        assert np.max(np.abs(got - want)) < 1e-5, rep
     for dt, wf in ((capi.DTYPE_COMPLEX, capi.SIG_COS), (capi.DTYPE_FLOAT, capi.SIG_COS), (capi.DTYPE_FLOAT, capi.SIG_SIN)):
         src = blocks.clSignalSource(dt, *GPU, 48000.0, wf, 1234.5, 0.75)
         inc = 6.28318530717958647692 * 1234.5 / 48000.0
