@@ -16,9 +16,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "liboracle.so")
 REF = os.path.join(_HERE, "_ref", "libref_firdes.so")
+REF_FILTERS = os.path.join(_HERE, "_ref", "libref_filters.so")
 
 _lib = None
 _ref = None
+_ref_filters = None
 
 _fp = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -110,6 +112,92 @@ def ref():
         R.ref_firdes_root_raised_cosine.restype = C.c_int
         _ref = R
     return _ref
+
+
+def ref_filters():
+    """The reference's own fft_filter_ccf / fir_filter_ccf / fft_complex (lib/fft_filter.cc, fir_filter.cc,
+    fft.cc compiled from /root/reference against oracle/shim/; None if never built)."""
+    global _ref_filters
+    if _ref_filters is None:
+        if not os.path.exists(REF_FILTERS):
+            return None
+        R = C.CDLL(REF_FILTERS)
+        R.ref_fftfilt_create.argtypes = [C.c_int, _fp, C.c_int]
+        R.ref_fftfilt_create.restype = C.c_void_p
+        R.ref_fftfilt_destroy.argtypes = [C.c_void_p]
+        R.ref_fftfilt_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        R.ref_fftfilt_set_taps.argtypes = [C.c_void_p, _fp, C.c_int]
+        R.ref_fftfilt_set_taps.restype = C.c_int
+        R.ref_fftfilt_filter.argtypes = [C.c_void_p, C.c_int, _fp, _fp]
+        R.ref_fftfilt_filter.restype = C.c_int
+        R.ref_fftfilt_xformed_taps.argtypes = [C.c_void_p, _fp]
+        R.ref_fir_ccf.argtypes = [_fp, C.c_int, _fp, C.c_long, C.c_int, _fp]
+        R.ref_fir_ccf.restype = C.c_int
+        R.ref_fft_complex.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_long]
+        R.ref_fft_complex.restype = C.c_int
+        _ref_filters = R
+    return _ref_filters
+
+
+class RefFftFilter:
+    """The reference's fft_filter_ccf object itself (oracle/_ref/libref_filters.so)."""
+
+    def __init__(self, taps, decim=1):
+        self.R = ref_filters()
+        assert self.R is not None, "oracle/_ref/libref_filters.so missing (make -C oracle where /root/reference exists)"
+        t = np.ascontiguousarray(taps, np.float32)
+        self.decim = decim
+        self.h = self.R.ref_fftfilt_create(decim, t, t.size)
+        assert self.h
+        a, b = C.c_int(), C.c_int()
+        self.R.ref_fftfilt_sizes(self.h, C.byref(a), C.byref(b))
+        self.fftsize, self.nsamples = a.value, b.value
+
+    def set_taps(self, taps):
+        t = np.ascontiguousarray(taps, np.float32)
+        self.nsamples = self.R.ref_fftfilt_set_taps(self.h, t, t.size)
+        a, b = C.c_int(), C.c_int()
+        self.R.ref_fftfilt_sizes(self.h, C.byref(a), C.byref(b))
+        self.fftsize = a.value
+
+    def xformed_taps(self):
+        out = np.zeros(self.fftsize, np.complex64)
+        self.R.ref_fftfilt_xformed_taps(self.h, _f(out))
+        return out
+
+    def filter(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        assert x.size % self.nsamples == 0 and x.size % self.decim == 0
+        nout = x.size // self.decim
+        out = np.zeros(nout + self.nsamples, np.complex64)
+        self.R.ref_fftfilt_filter(self.h, nout, _f(x), _f(out))
+        return out[:nout]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.ref_fftfilt_destroy(self.h)
+            self.h = None
+
+
+def ref_fir(x_with_history, taps, decim=1):
+    """The reference's fir_filter_ccf::filterN / filterNdec on K-1 history samples + new samples."""
+    R = ref_filters()
+    taps = np.ascontiguousarray(taps, np.float32)
+    x = np.ascontiguousarray(x_with_history, np.complex64)
+    nin = x.size - (taps.size - 1)
+    n = (nin + decim - 1) // decim
+    out = np.zeros(n, np.complex64)
+    assert R.ref_fir_ccf(taps, taps.size, _f(x), n, decim, _f(out)) == 0
+    return out
+
+
+def ref_fft(x, n, direction=-1):
+    """The reference's fft_complex plan wrapper (over the shim transform) on nvec vectors."""
+    R = ref_filters()
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros_like(x)
+    assert R.ref_fft_complex(n, int(direction < 0), _f(x), _f(out), x.size // n) == 0
+    return out
 
 
 def _f(a):

@@ -6,13 +6,23 @@
  * against and the "port" CPU baseline that bench.py times; nothing under
  * gr_clenabled_b200/ may link, import or call it.
  *
- * PARITY PINNING: the reference ships no golden outputs for this path and its
- * own CPU code (FFTW3f, VOLK, GNU Radio) cannot be built in this image, so the
- * float FFT/filter/PFB/X-engine functions here are "parity unpinned" except for
- * (a) the reference's known-answer inputs (const (1.0,0.5)*2, the sin/cos tone,
- * ramp taps -- tests/test_oracle.py) and (b) the window/firdes tap design, which
- * IS pinned against the reference's own lib/window.cc + lib/firdes.cc compiled
- * into oracle/_ref/libref_firdes.so (oracle/Makefile).
+ * PARITY PINNING.  Pinned against the reference's OWN code compiled here from
+ * /root/reference (oracle/Makefile -> oracle/_ref/, vectors under tests/golden/):
+ *   - window / firdes tap design: lib/window.cc + lib/firdes.cc
+ *     (libref_firdes.so, ref_firdes_window.npz);
+ *   - fft_filter_ccf, fir_filter_ccf and the fft_complex plan wrapper:
+ *     lib/fft_filter.cc + lib/fir_filter.cc + lib/fft.cc against the stand-in
+ *     VOLK / FFTW3 / Boost headers of oracle/shim/ (libref_filters.so,
+ *     ref_filters.npz): blocking, overlap-add tail, tap reversal, decimation
+ *     counters are the reference's code; the innermost library kernels (FFT
+ *     butterflies, dot products) are the shim's;
+ *   - numeric ids: include/clenabled/*.h + grc/*.yml (ref_constants.json).
+ * Still "parity unpinned" by reference outputs (every *_impl.cc needs GNU Radio,
+ * OpenCL and clFFT, and its arithmetic lives in OpenCL C strings): the FFT
+ * butterflies themselves, the polyphase channelizer and the X-engine; they rest
+ * on the reference tools' known-answer inputs (const (1.0,0.5)*2, the sin/cos
+ * tone, ramp taps) and on independent implementations of the published maths
+ * (pocketfft, scipy.signal, exact int64 einsum) -- tests/test_oracle.py.
  *
  * Every function cites the reference file:line it follows
  * (paths relative to the reference tree).

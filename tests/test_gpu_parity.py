@@ -233,6 +233,29 @@ def test_filter_matches_reference_overlap_add(golden):
     assert blocks.filter_ref_sizes(256) == (512, 257)
 
 
+@pytest.mark.parametrize("name", ["lp256_d1", "lp256_d4", "ramp256_d1", "short37_d3", "one_tap"])
+def test_filter_matches_reference_build_vectors(golden, name):
+    """the CUDA clFilter (both modes) against outputs of the reference's OWN fft_filter_ccf / fir_filter_ccf
+    objects (tests/golden/ref_filters.npz, produced by oracle/_ref/libref_filters.so = lib/fft_filter.cc +
+    lib/fir_filter.cc + lib/fft.cc compiled from the reference tree), fed in the same calls"""
+    meta = golden[name + "_meta"]
+    D, seed, n, fftsize, nsamples = (int(v) for v in meta[:5])
+    calls = [int(v) for v in meta[5:]]
+    taps = golden[name + "_taps"]
+    assert blocks.filter_ref_sizes(taps.size) == (fftsize, nsamples)
+    x = orc.rng_c32(n, seed)
+    for use_time in (False, True):
+        blk = blocks.clFilter(*GPU, D, taps, 1, 0, use_time)
+        unit, pos, ys = nsamples * D, 0, []
+        for c in calls:
+            ys.append(blk.work(x[pos:pos + c * unit]))
+            pos += c * unit
+        got = np.concatenate(ys)
+        assert got.size == golden[name + "_fft"].size
+        assert rel_err(got, golden[name + "_fft"]) < TOL, use_time
+        assert rel_err(got, golden[name + "_fir"]) < TOL, use_time
+
+
 @pytest.mark.parametrize("ntaps", [1, 2, 31, 300, 1000, 3000])
 def test_filter_tap_counts(ntaps):
     taps = (orc.rng_f32(ntaps, orc.SEED_L + 2) / ntaps).astype(np.float32)

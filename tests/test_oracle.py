@@ -4,7 +4,10 @@ The reference ships no golden outputs for the hot path, so the oracl
 is pinned three ways:
   1. against the reference's OWN code where it compiles here: lib/window.cc and
      lib/firdes.cc via oracle/_ref (live when present, and always against the
-     committed vectors tests/golden/ref_firdes_window.npz generated from it);
+     committed vectors tests/golden/ref_firdes_window.npz generated from it); and
+     lib/fft_filter.cc + lib/fir_filter.cc + lib/fft.cc (fft_filter_ccf, fir_filter_ccf,
+     fft_complex) compiled against the stand-in VOLK/FFTW3/Boost headers of oracle/shim/
+     (oracle/_ref/libref_filters.so; vectors in tests/golden/ref_filters.npz);
   2. against the reference tools' known-answer inputs (tests/golden/kat.npz);
   3. against independent implementations of the published maths: numpy's pocketfft,
      scipy.signal.lfilter/upfirdn, exact int64 numpy einsum.
@@ -195,6 +198,75 @@ def _pfb_direct(x, taps, M, R, ch_map, niter):
         spec = np.array([np.sum(filt * np.exp(2j * np.pi * n * c / M)) for c in range(M)])
         out[i] = spec[list(ch_map)]
     return out.reshape(-1)
+
+
+REF_FILTER_CASES = ["lp256_d1", "lp256_d4", "ramp256_d1", "short37_d3", "one_tap"]
+
+
+def _ref_case(golden, name):
+    meta = golden[name + "_meta"]
+    D, seed, n, fftsize, nsamples = (int(v) for v in meta[:5])
+    calls = [int(v) for v in meta[5:]]
+    return golden[name + "_taps"], D, seed, n, fftsize, nsamples, calls
+
+
+@pytest.mark.parametrize("name", REF_FILTER_CASES)
+def test_oracle_filters_match_reference_build_vectors(golden, name):
+    """oracle_c.c's fft_filter_ccf / fir_filter_ccf restatement against outputs of the reference's OWN classes
+    (tests/golden/ref_filters.npz, made by tests/golden/make_ref_filters.py from oracle/_ref/libref_filters.so):
+    same sizes, same transformed taps, same outputs over several calls (tail and decimation phase carried)."""
+    taps, D, seed, n, fftsize, nsamples, calls = _ref_case(golden, name)
+    assert orc.fftfilt_sizes(taps.size) == (fftsize, nsamples)
+    x = orc.rng_c32(n, seed)
+    f = orc.FftFilter(taps, D)
+    unit, pos, ys = nsamples * D, 0, []
+    for c in calls:
+        ys.append(f.filter(x[pos:pos + c * unit]))
+        pos += c * unit
+    got = np.concatenate(ys)
+    want = golden[name + "_fft"]
+    assert got.size == want.size
+    assert rel_err(got, want) < 1e-6
+    fir = orc.fir(np.concatenate([np.zeros(taps.size - 1, np.complex64), x]), taps, D)
+    assert fir.size == golden[name + "_fir"].size
+    assert rel_err(fir, golden[name + "_fir"]) < 1e-6
+    # the transformed taps: H[k] = FFT(taps / fftsize) (fft_filter.cc:52-63)
+    H = np.fft.fft(np.concatenate([taps.astype(np.float64) / fftsize, np.zeros(fftsize - taps.size)]))
+    assert rel_err(golden[name + "_H"], H) < 1e-6
+
+
+@pytest.mark.skipif(orc.ref_filters() is None, reason="oracle/_ref/libref_filters.so not built")
+@pytest.mark.parametrize("ntaps,D", [(1, 1), (2, 2), (31, 1), (256, 1), (256, 3), (300, 2), (1000, 1)])
+def test_oracle_filters_match_live_reference_build(ntaps, D):
+    """the same comparison against the reference classes run live (random taps, more shapes, tap swap)"""
+    taps = (orc.rng_f32(ntaps, 4242 + ntaps) / ntaps).astype(np.float32)
+    rf, of = orc.RefFftFilter(taps, D), orc.FftFilter(taps, D)
+    assert (rf.fftsize, rf.nsamples) == (of.fftsize, of.nsamples)
+    unit = rf.nsamples * D
+    x = orc.rng_c32(unit * 7, 4300 + ntaps)
+    a = np.concatenate([rf.filter(x[:unit * 3]), rf.filter(x[unit * 3:])])
+    b = np.concatenate([of.filter(x[:unit * 3]), of.filter(x[unit * 3:])])
+    assert rel_err(b, a) < 1e-6
+    xh = np.concatenate([np.zeros(ntaps - 1, np.complex64), x])
+    assert rel_err(orc.fir(xh, taps, D), orc.ref_fir(xh, taps, D)) < 1e-6
+    # both reference classes compute the same stream (zero-state convolution)
+    assert rel_err(a, orc.ref_fir(xh, taps, D)[:a.size]) < 1e-5
+    xv = orc.rng_c32(1024 * 3, 4400)
+    for d in (-1, 1):
+        assert rel_err(orc.fft(xv, 1024, d), orc.ref_fft(xv, 1024, d)) < 1e-6
+
+
+@pytest.mark.skipif(orc.ref_filters() is None, reason="oracle/_ref/libref_filters.so not built")
+def test_filter_fixture_is_what_the_live_reference_build_gives(golden):
+    for name in REF_FILTER_CASES:
+        taps, D, seed, n, fftsize, nsamples, calls = _ref_case(golden, name)
+        f = orc.RefFftFilter(taps, D)
+        x = orc.rng_c32(n, seed)
+        unit, pos, ys = nsamples * D, 0, []
+        for c in calls:
+            ys.append(f.filter(x[pos:pos + c * unit]))
+            pos += c * unit
+        assert np.array_equal(np.concatenate(ys), golden[name + "_fft"])
 
 
 @pytest.mark.parametrize("M,R,T", [(8, 8, 24), (8, 4, 19), (64, 64, 128)])
