@@ -357,6 +357,34 @@ class clXEngine(_Block):
         check(self._lib.clb200_xengine_work_i32(self._h, _ptr(buf), _ptr(out)))
         return out
 
+    # ---- streaming ingest: the general_work() shape of the reference block (work_processor / runThread) ----
+    def stream_begin(self, pipeline_integration=0, result_slots=4):
+        check(self._lib.clb200_xengine_stream_begin(self._h, int(pipeline_integration), int(result_slots)))
+
+    def push(self, ports, ntime):
+        """ports: one array (or raw address) per input stream holding `ntime` items each"""
+        keep = [p if isinstance(p, int) else np.ascontiguousarray(p) for p in ports]
+        a = (C.c_void_p * len(keep))(*[p if isinstance(p, int) else p.ctypes.data for p in keep])
+        check(self._lib.clb200_xengine_push_timesteps(self._h, a, len(keep), int(ntime)))
+
+    def poll(self, wait=False, out=None):
+        """the oldest finished visibility matrix, or None if none is ready"""
+        if out is None:
+            out = np.zeros(self.output_items(), c64)
+        ready = C.c_int(0)
+        check(self._lib.clb200_xengine_poll_result(self._h, _ptr(out), int(wait), C.byref(ready)))
+        return out if ready.value else None
+
+    def stream_state(self):
+        t, n, r = C.c_long(), C.c_long(), C.c_long()
+        p, b = C.c_uint64(), C.c_uint64()
+        check(self._lib.clb200_xengine_stream_state(self._h, C.byref(t), C.byref(n), C.byref(r), C.byref(p), C.byref(b)))
+        return {"tracker": t.value, "integrations": n.value, "results_pending": r.value,
+                "pushes": p.value, "pushes_blocked": b.value}
+
+    def stream_end(self):
+        check(self._lib.clb200_xengine_stream_end(self._h))
+
     def launch_device(self, d_in, d_out, accumulate=False, stream=0):
         check(self._lib.clb200_xengine_launch_device(self._h, d_in, d_out, int(accumulate), stream))
 

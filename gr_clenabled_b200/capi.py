@@ -82,6 +82,8 @@ SIGNATURES = {
     "clb200_pfb_create": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _i, _ph]),
     "clb200_pfb_work": (_i, [_vp, _vp, _vp, _l]),
     "clb200_pfb_launch_device": (_i, [_vp, _vp, _vp, _l, _vp]),
+    "clb200_describe": (_i, [_vp, C.c_char_p, _i]),
+    "clb200_set_debug": (_i, [_vp, _i]),
     "clb200_xengine_create": (_i, [_i, _i, _i, _i, _i, _i, _ph]),
     "clb200_xengine_input_bytes": (_l, [_vp]),
     "clb200_xengine_output_items": (_l, [_vp]),
@@ -89,6 +91,11 @@ SIGNATURES = {
     "clb200_xengine_work_i32": (_i, [_vp, _vp, _vp]),
     "clb200_xengine_launch_device": (_i, [_vp, _vp, _vp, _i, _vp]),
     "clb200_xengine_launch_device_i32": (_i, [_vp, _vp, _vp, _vp]),
+    "clb200_xengine_stream_begin": (_i, [_vp, _i, _i]),
+    "clb200_xengine_push_timesteps": (_i, [_vp, _ph, _i, _l]),
+    "clb200_xengine_poll_result": (_i, [_vp, _vp, _i, _pi]),
+    "clb200_xengine_stream_state": (_i, [_vp, _pl, _pl, _pl, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "clb200_xengine_stream_end": (_i, [_vp]),
     "clb200_xengine_set_shard": (_i, [_vp, _i, _i]),
     "clb200_xengine_set_gather": (_i, [_vp, _i, _ph]),
     "clb200_xengine_launch_device_gather": (_i, [_vp, _vp, _vp]),

@@ -7,6 +7,7 @@
 // a thread-local message.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -14,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 
 #include "../../include/clenabled_b200.h"
 
@@ -44,6 +46,12 @@ void set_error(const char *fmt, ...);
         int _rc = (expr);                                                           \
         if (_rc != CLB200_OK) return _rc;                                           \
     } while (0)
+
+// NVTX range for the host-path phases (H2D / kernels / D2H); a no-op unless a profiler is attached
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 enum BlockKind {
     KIND_MATHCONST = 1, KIND_MATHOP, KIND_UNARY, KIND_SNR, KIND_C2MAGPHASE, KIND_MAGPHASE2C,
@@ -84,6 +92,9 @@ struct clb200_block {
     clb200::Slot slot[clb200::NSLOT];
     bool slots_ready = false;
     uint64_t n_h2d = 0, n_d2h = 0, n_launch = 0;
+    std::string info;               // kernel variant and launch geometry, filled by create (clb200_describe)
+    int debug = 0;                  // setDebug of the reference factories (clb200_set_debug)
+    void set_info(const char *fmt, ...);
     virtual ~clb200_block();
     int init_slots();
 };
@@ -114,6 +125,13 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
 {
     if (total_out) *total_out = 0;
     if (nitems <= 0) return CLB200_OK;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto debug_line = [&](const char *route, long chunks, long n_out) {
+        if (!b->debug) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count();
+        fprintf(stderr, "clenabled_b200[debug] kind %d: work(%ld items) -> %ld items, %s, %ld chunk(s), %.1f us\n", b->kind,
+                nitems, n_out, route, chunks, us);
+    };
     CLB_TRY(b->init_slots());
     bool pin_i[MAXPORT], pin_o[MAXPORT];
     for (int k = 0; k < pd.nin; k++) pin_i[k] = is_pinned(pd.in[k]);
@@ -153,6 +171,7 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
                 }
             }
             long n_out = nitems;
+            NvtxRange r("clb200 small call: kernel over pinned host memory");
             CLB_TRY(launch(d_in, d_out, nitems, s.stream, &n_out));
             CLB_CUDA(cudaStreamSynchronize(s.stream));
             for (int k = 0; k < pd.nout; k++) {
@@ -160,6 +179,7 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
                 b->n_d2h += (size_t)n_out * pd.out_bytes[k];
             }
             if (total_out) *total_out = n_out;
+            debug_line("zero-copy (kernel reads/writes pinned host memory)", 1, n_out);
             return CLB200_OK;
         }
     }
@@ -195,6 +215,7 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
     for (long first = 0; first < nitems; first += chunk_items, c++) {
         long n = std::min(chunk_items, nitems - first);
         Slot &s = b->slot[c % NSLOT];
+        NvtxRange r("clb200 chunk: H2D + kernel + D2H enqueue");
         CLB_TRY(drain(s));
         const void *d_in[MAXPORT];
         void *d_out[MAXPORT];
@@ -240,6 +261,7 @@ int run_chunked(clb200_block *b, const PortDesc &pd, long nitems, long chunk_ite
     for (long i = 0; i < NSLOT; i++) CLB_TRY(drain(b->slot[(c + i) % NSLOT]));
     guard.armed = false;
     if (total_out) *total_out = out_pos;
+    debug_line("copy engines, 3 slots", c, out_pos);
     return CLB200_OK;
 }
 

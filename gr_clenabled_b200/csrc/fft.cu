@@ -617,6 +617,10 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
             f->use_pf = true;
         cudaGetLastError();
     }
+    f->set_info("clFFT %d-pt %s%s%s%s: k_fft<%d,%d,%d,...> %d threads, %d transform(s)/CTA, %d B shared memory, %d CTAs/SM -> persistent grid of %d",
+                fft_size, dir < 0 ? "forward" : "backward", dtype == CLB200_DTYPE_FLOAT ? ", real input" : "",
+                f->has_window ? ", window fused" : "", f->shift ? ", half swap fused" : "", f->var->logn, f->var->ept, f->var->batch,
+                f->var->threads, f->var->batch, f->var->smem_bytes, f->resident, f->resident * device_sm_count(device));
     *out = f;
     return CLB200_OK;
 }

@@ -374,6 +374,14 @@ int filter_configure(Filter *f, const std::vector<float> &taps)
         CLB_CHECK(occ >= 1, CLB200_ECUDA, "clFilter: FFT-filter kernel does not fit an SM");
         f->resident = occ;
     }
+    if (f->time_kernel)
+        f->set_info("clFilter %d taps, decimation %d: time-domain k_fir_d1 (register sliding window, taps + %d-sample tile in shared "
+                    "memory), %d threads, %d CTAs/SM", K, f->decim, FIR_TILE, FIR_THREADS, f->resident);
+    else
+        f->set_info("clFilter %d taps, decimation %d: overlap-save k_fftfilt, %d-pt blocks (%d new outputs each; the reference blocks "
+                    "%d/%d), %d threads, %d B shared memory, %d CTAs/SM", K, f->decim, 1 << f->var->logn, (1 << f->var->logn) - K + 1,
+                    (int)(2 * pow(2.0, ceil(log((double)K) / log(2.0)))), (int)(2 * pow(2.0, ceil(log((double)K) / log(2.0)))) - K + 1,
+                    f->var->threads, f->var->smem_bytes, f->resident);
     return CLB200_OK;
 }
 

@@ -276,6 +276,10 @@ int clb200_pfb_create(int device, const float *taps, int ntaps, int buf_items, i
         return fail(CLB200_ECUDA);
     }
     p->resident = occ;
+    p->set_info("clPolyphaseChannelizer %d channels, %d taps, %d inputs/iteration, %d mapped outputs: %d-pt inverse FFT per time step, "
+                "%d threads/CTA, %d B shared memory, %d CTAs/SM%s",
+                num_channels, ntaps, ninputs_per_iter, nmap, num_channels, p->var->threads, p->var->smem_bytes, p->resident,
+                p->identity ? ", identity map (direct stores)" : ", channel map through shared memory");
     *out = p;
     return CLB200_OK;
 }

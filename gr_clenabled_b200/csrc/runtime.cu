@@ -93,6 +93,16 @@ bool is_pinned(const void *p)
 
 using namespace clb200;
 
+void clb200_block::set_info(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    info = buf;
+}
+
 int clb200_block::init_slots()
 {
     if (slots_ready) return CLB200_OK;
@@ -193,6 +203,21 @@ int clb200_destroy(clb200_handle h)
 {
     if (!h) return CLB200_OK;
     delete h;
+    return CLB200_OK;
+}
+
+int clb200_describe(clb200_handle h, char *buf, int buflen)
+{
+    CLB_CHECK(h != nullptr && buf != nullptr && buflen > 0, CLB200_EINVAL, "bad arguments");
+    snprintf(buf, buflen, "device %d, %d SMs: %s", h->device, device_sm_count(h->device),
+             h->info.empty() ? "(no description)" : h->info.c_str());
+    return CLB200_OK;
+}
+
+int clb200_set_debug(clb200_handle h, int on)
+{
+    CLB_CHECK(h != nullptr, CLB200_EINVAL, "null handle");
+    h->debug = on ? 1 : 0;
     return CLB200_OK;
 }
 

@@ -465,6 +465,23 @@ struct XEngine : clb200_block {
     Buf pin_in[2], pin_out;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
+    // ---- streaming ingest (clb200_xengine_stream_begin / push_timesteps / poll_result) ----
+    static constexpr int MAXRES = 8;
+    struct Stream {
+        bool on = false;
+        int pipeline = 1, nres = 4;
+        Buf pin[2], dev[2];                    // the integration being filled / the one being correlated
+        Buf d_res[MAXRES], pin_res[MAXRES];    // result ring: device matrix + its pinned host copy
+        cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+        cudaEvent_t ev_h2d[2] = {}, ev_kern[2] = {};          // uploads of buffer b landed / kernel on buffer b done
+        cudaEvent_t ev_kres[MAXRES] = {}, ev_res[MAXRES] = {}; // matrix r computed / copied to the host
+        bool pin_dirty[2] = {false, false};    // pinned staging b still has uploads in flight
+        long tracker = 0;                      // time steps of the current integration ingested so far
+        long n_integ = 0;                      // integrations handed to the GPU
+        long res_head = 0, res_tail = 0;       // results launched / delivered
+        int pipe_count = 0;
+        uint64_t n_push = 0, n_blocked = 0;    // push calls / calls that had to wait for the GPU
+    } st;
     long nbl() const { return (long)A * (A + 1) / 2; }
     long out_items() const { return (long)F * nbl() * npol * npol; }
     size_t sample_bytes() const
@@ -487,8 +504,30 @@ struct XEngine : clb200_block {
         d_out.release();
         pin_out.release();
         if (ev_done) cudaEventDestroy(ev_done);
+        stream_free();
         if (s_copy) cudaStreamDestroy(s_copy);
         if (s_comp) cudaStreamDestroy(s_comp);
+    }
+    void stream_free()
+    {
+        if (st.s_h2d) cudaStreamSynchronize(st.s_h2d);
+        if (s_comp) cudaStreamSynchronize(s_comp);
+        if (st.s_d2h) cudaStreamSynchronize(st.s_d2h);
+        for (int b = 0; b < 2; b++) {
+            st.pin[b].release();
+            st.dev[b].release();
+            if (st.ev_h2d[b]) cudaEventDestroy(st.ev_h2d[b]);
+            if (st.ev_kern[b]) cudaEventDestroy(st.ev_kern[b]);
+        }
+        for (int r = 0; r < MAXRES; r++) {
+            st.d_res[r].release();
+            st.pin_res[r].release();
+            if (st.ev_kres[r]) cudaEventDestroy(st.ev_kres[r]);
+            if (st.ev_res[r]) cudaEventDestroy(st.ev_res[r]);
+        }
+        if (st.s_h2d) cudaStreamDestroy(st.s_h2d);
+        if (st.s_d2h) cudaStreamDestroy(st.s_d2h);
+        st = Stream();
     }
 };
 
@@ -721,6 +760,175 @@ int xe_work(XEngine *x, const void *in, void *out, bool want_i32, int accumulate
     return CLB200_OK;
 }
 
+// ---- streaming ingest --------------------------------------------------------------------------
+// The reference marshals every general_work() call into one of two pinned integration buffers and a worker
+// thread uploads + correlates a FULL buffer while the scheduler thread fills the other one
+// (work_processor lib/clXEngine_impl.cc:918-1142, runThread :1234-1299).  Here every push is DMA'd at
+// once on a copy stream, so that when the last time step of an integration arrives only that last piece,
+// the kernel and the result read-back remain; nothing in push() waits for the GPU unless the GPU is a
+// whole integration behind (back-pressure), and results are picked up later with poll_result().
+int xe_stream_begin(XEngine *x, int pipeline, int nres)
+{
+    XEngine::Stream &st = x->st;
+    CLB_CHECK(!st.on, CLB200_ESTATE, "clXEngine: stream already begun");
+    CLB_CHECK(nres >= 2 && nres <= XEngine::MAXRES, CLB200_EINVAL, "clXEngine: result slots must be 2..%d", XEngine::MAXRES);
+    CLB_TRY(xe_init_streams(x));
+    st.pipeline = pipeline > 1 ? pipeline : 1;
+    st.nres = nres;
+    const size_t in_bytes = (size_t)x->T * x->A * x->F * x->npol * x->sample_bytes();      // this handle's slab
+    const size_t out_bytes = (size_t)x->out_items() * 8;
+    CLB_CUDA(cudaStreamCreateWithFlags(&st.s_h2d, cudaStreamNonBlocking));
+    CLB_CUDA(cudaStreamCreateWithFlags(&st.s_d2h, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        st.pin[b].host = true;
+        CLB_TRY(st.pin[b].reserve(in_bytes));
+        CLB_TRY(st.dev[b].reserve(in_bytes));
+        CLB_CUDA(cudaEventCreateWithFlags(&st.ev_h2d[b], cudaEventDisableTiming));
+        CLB_CUDA(cudaEventCreateWithFlags(&st.ev_kern[b], cudaEventDisableTiming));
+    }
+    for (int r = 0; r < nres; r++) {
+        st.pin_res[r].host = true;
+        CLB_TRY(st.pin_res[r].reserve(out_bytes));
+        CLB_TRY(st.d_res[r].reserve(out_bytes));
+        CLB_CUDA(cudaEventCreateWithFlags(&st.ev_kres[r], cudaEventDisableTiming));
+        CLB_CUDA(cudaEventCreateWithFlags(&st.ev_res[r], cudaEventDisableTiming));
+    }
+    if (x->data_type != CLB200_DTYPE_COMPLEX) CLB_TRY(x->d_acc.reserve(out_bytes));
+    st.on = true;
+    return CLB200_OK;
+}
+
+// hand the integration in buffer b to the GPU: kernel after its uploads, result read-back after the kernel
+int xe_stream_launch(XEngine *x, int b)
+{
+    XEngine::Stream &st = x->st;
+    const int r = (int)(st.res_head % st.nres);
+    const bool first_of_group = st.pipe_count == 0;
+    CLB_CUDA(cudaEventRecord(st.ev_h2d[b], st.s_h2d));
+    CLB_CUDA(cudaStreamWaitEvent(x->s_comp, st.ev_h2d[b], 0));
+    if (first_of_group && st.res_head >= st.nres)                       // matrix r is being rewritten: its last read-back is over
+        CLB_CUDA(cudaStreamWaitEvent(x->s_comp, st.ev_res[r], 0));
+    CLB_TRY(xe_launch(x, st.dev[b].p, x->T, x->F, 0, nullptr, (float2 *)st.d_res[r].p, first_of_group ? 0 : 1, x->s_comp));
+    CLB_CUDA(cudaEventRecord(st.ev_kern[b], x->s_comp));
+    st.n_integ++;
+    if (++st.pipe_count >= st.pipeline) {                               // pipeline_integration (:785-808): emit every Nth
+        st.pipe_count = 0;
+        CLB_CUDA(cudaEventRecord(st.ev_kres[r], x->s_comp));
+        CLB_CUDA(cudaStreamWaitEvent(st.s_d2h, st.ev_kres[r], 0));
+        CLB_CUDA(cudaMemcpyAsync(st.pin_res[r].p, st.d_res[r].p, (size_t)x->out_items() * 8, cudaMemcpyDeviceToHost, st.s_d2h));
+        CLB_CUDA(cudaEventRecord(st.ev_res[r], st.s_d2h));
+        x->n_d2h += (size_t)x->out_items() * 8;
+        st.res_head++;
+    }
+    return CLB200_OK;
+}
+
+// ports: the block's input streams for `ntime` time steps -- ports[s] holds ntime items of this station
+// (row = all channels of the caller's stream); two polarisations of unpacked data arrive as separate ports
+// X = ports[s], Y = ports[s + A] and are interleaved per channel (:1010-1057)
+int xe_stream_push(XEngine *x, const void *const *ports, int nports, long ntime)
+{
+    XEngine::Stream &st = x->st;
+    CLB_CHECK(st.on, CLB200_ESTATE, "clXEngine: stream_begin first");
+    const bool planar_pol = x->npol == 2 && x->data_type != CLB200_DTYPE_PACKEDXY;
+    const int need = planar_pol ? 2 * x->A : x->A;
+    CLB_CHECK(nports == need, CLB200_EINVAL, "clXEngine: %d ports given, %d expected", nports, need);
+    const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
+    const size_t sb = x->sample_bytes();
+    const size_t vec_in = (size_t)Ftot * sb * (planar_pol ? 1 : x->npol);     // bytes of one port item
+    const size_t off_in = (size_t)x->f_first * sb * (planar_pol ? 1 : x->npol);
+    const size_t row = (size_t)x->F * x->npol * sb;                            // one station, one time step (slab)
+    const size_t frame = row * x->A;
+    st.n_push++;
+    long done = 0;
+    while (done < ntime) {
+        const int b = (int)((st.n_integ) & 1);
+        const long n = std::min<long>(ntime - done, x->T - st.tracker);
+        // zero-copy route: every port is page-locked (clb200_register_host_buffer) and no interleave is needed ->
+        // the copy engine gathers the rows straight out of the ports; the call returns after the DMA has read them
+        bool direct = !planar_pol && (size_t)n * frame >= ((size_t)1 << 20);
+        for (int s = 0; direct && s < x->A; s++) direct = is_pinned(ports[s]);
+        if (st.tracker == 0 && st.pipe_count == 0)
+            // checked before anything of the integration is consumed, so that a refused push changes nothing
+            CLB_CHECK(st.res_head - st.res_tail < st.nres, CLB200_ESTATE,
+                      "clXEngine: %d results pending -- poll_result() before pushing more", st.nres);
+        if (st.tracker == 0 && st.n_integ >= 2) {
+            // buffer b was last used by integration n_integ-2: its kernel must be done before the copy stream
+            // overwrites the device buffer (stream-ordered), and its uploads before the host overwrites the staging
+            CLB_CUDA(cudaStreamWaitEvent(st.s_h2d, st.ev_kern[b], 0));
+            if (st.pin_dirty[b]) {
+                if (cudaEventQuery(st.ev_h2d[b]) != cudaSuccess) {
+                    st.n_blocked++;
+                    CLB_CUDA(cudaEventSynchronize(st.ev_h2d[b]));
+                }
+                st.pin_dirty[b] = false;
+            }
+        }
+        char *dst_dev = (char *)st.dev[b].p + (size_t)st.tracker * frame;
+        if (direct) {
+            for (int s = 0; s < x->A; s++)
+                CLB_CUDA(cudaMemcpy2DAsync(dst_dev + s * row, frame, (const char *)ports[s] + (size_t)done * vec_in + off_in,
+                                           vec_in, row, (size_t)n, cudaMemcpyHostToDevice, st.s_h2d));
+        } else {
+            char *stage = (char *)st.pin[b].p + (size_t)st.tracker * frame;
+            for (long t = 0; t < n; t++) {
+                char *d = stage + (size_t)t * frame;
+                for (int s = 0; s < x->A; s++) {
+                    if (!planar_pol) {
+                        memcpy(d + s * row, (const char *)ports[s] + (size_t)(done + t) * vec_in + off_in, row);
+                    } else {
+                        const char *px = (const char *)ports[s] + (size_t)(done + t) * vec_in + off_in;
+                        const char *py = (const char *)ports[s + x->A] + (size_t)(done + t) * vec_in + off_in;
+                        char *o = d + s * row;
+                        if (sb == 2) {
+                            for (int c = 0; c < x->F; c++) {
+                                memcpy(o + 4 * c, px + 2 * c, 2);
+                                memcpy(o + 4 * c + 2, py + 2 * c, 2);
+                            }
+                        } else {
+                            for (int c = 0; c < x->F; c++) {
+                                memcpy(o + 2 * c * sb, px + c * sb, sb);
+                                memcpy(o + (2 * c + 1) * sb, py + c * sb, sb);
+                            }
+                        }
+                    }
+                }
+            }
+            CLB_CUDA(cudaMemcpyAsync(dst_dev, stage, (size_t)n * frame, cudaMemcpyHostToDevice, st.s_h2d));
+            st.pin_dirty[b] = true;
+        }
+        x->n_h2d += (size_t)n * frame;
+        st.tracker += n;
+        done += n;
+        if (direct) CLB_CUDA(cudaStreamSynchronize(st.s_h2d));        // the ports are the caller's again on return
+        if (st.tracker == x->T) {
+            CLB_TRY(xe_stream_launch(x, b));
+            st.tracker = 0;
+        }
+    }
+    return CLB200_OK;
+}
+
+int xe_stream_poll(XEngine *x, void *out_c32, int wait, int *ready)
+{
+    XEngine::Stream &st = x->st;
+    CLB_CHECK(st.on, CLB200_ESTATE, "clXEngine: stream_begin first");
+    *ready = 0;
+    if (st.res_tail >= st.res_head) return CLB200_OK;
+    const int r = (int)(st.res_tail % st.nres);
+    if (wait) {
+        CLB_CUDA(cudaEventSynchronize(st.ev_res[r]));
+    } else {
+        cudaError_t e = cudaEventQuery(st.ev_res[r]);
+        if (e == cudaErrorNotReady) return CLB200_OK;
+        CLB_CUDA(e);
+    }
+    if (out_c32) memcpy(out_c32, st.pin_res[r].p, (size_t)x->out_items() * 8);
+    st.res_tail++;
+    *ready = 1;
+    return CLB200_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -791,6 +999,13 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
         delete x;
         return CLB200_ECUDA;
     }
+    x->set_info("clXEngine %d inputs x %d pol, %d channels, %d time steps, data type %d: %s", num_inputs, npol, num_channels,
+                integration, data_type,
+                data_type == CLB200_DTYPE_COMPLEX ? "tiled FP32 kernel (complex float input)"
+                : x->use_tma ? "k_xengine_tma: TMA boxes -> LDSM/STSM byte transposes -> tcgen05.mma kind::i8 (s32 in TMEM), "
+                               "16 (or 8) channels per CTA, time slices as thread-block clusters"
+                : x->use_tc ? "k_xengine_tc: LDG-fed tcgen05.mma kind::i8"
+                            : "k_xengine_i8: mma.sync m16n8k32 (33..64 input rows)");
     *out = x;
     return CLB200_OK;
 }
@@ -886,6 +1101,62 @@ int clb200_xengine_launch_device_i32(clb200_handle h, const void *d_in, int32_t 
     DeviceGuard g(x->device);
     const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
     return xe_launch(x, d_in, x->T, Ftot, x->f_first, d_out_i32, nullptr, 0, (cudaStream_t)stream);
+}
+
+int clb200_xengine_stream_begin(clb200_handle h, int pipeline_integration, int result_slots)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    DeviceGuard g(x->device);
+    std::lock_guard<std::mutex> lk(x->mtx);
+    int rc = xe_stream_begin(x, pipeline_integration, result_slots > 0 ? result_slots : 4);
+    if (rc != CLB200_OK) x->stream_free();
+    return rc;
+}
+
+int clb200_xengine_push_timesteps(clb200_handle h, const void *const *ports, int nports, long ntime)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(ports != nullptr && ntime >= 0, CLB200_EINVAL, "bad arguments");
+    for (int i = 0; i < nports; i++) CLB_CHECK(ports[i] != nullptr, CLB200_EINVAL, "null port %d", i);
+    DeviceGuard g(x->device);
+    std::lock_guard<std::mutex> lk(x->mtx);
+    return xe_stream_push(x, ports, nports, ntime);
+}
+
+int clb200_xengine_poll_result(clb200_handle h, void *out_c32, int wait, int *ready)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(ready != nullptr, CLB200_EINVAL, "null ready");
+    DeviceGuard g(x->device);
+    std::lock_guard<std::mutex> lk(x->mtx);
+    return xe_stream_poll(x, out_c32, wait, ready);
+}
+
+int clb200_xengine_stream_state(clb200_handle h, long *tracker, long *integrations, long *results_pending,
+                                uint64_t *pushes, uint64_t *pushes_blocked)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    std::lock_guard<std::mutex> lk(x->mtx);
+    if (tracker) *tracker = x->st.tracker;
+    if (integrations) *integrations = x->st.n_integ;
+    if (results_pending) *results_pending = x->st.res_head - x->st.res_tail;
+    if (pushes) *pushes = x->st.n_push;
+    if (pushes_blocked) *pushes_blocked = x->st.n_blocked;
+    return CLB200_OK;
+}
+
+int clb200_xengine_stream_end(clb200_handle h)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    DeviceGuard g(x->device);
+    std::lock_guard<std::mutex> lk(x->mtx);
+    x->stream_free();
+    return CLB200_OK;
 }
 
 } // extern "C"

@@ -7,6 +7,7 @@
 #ifndef CLB200_GR_STUB_BLOCK_H
 #define CLB200_GR_STUB_BLOCK_H
 #include <complex>
+#include <cstdio>
 #include <functional>
 #include <cstdint>
 #include <map>
@@ -46,6 +47,21 @@ private:
     io_signature(int mn, int mx, int sz) : d_min(mn), d_max(mx), d_size(sz) {}
     int d_min, d_max, d_size;
 };
+
+// gr::logger + GR_LOG_* (gnuradio/logger.h): records the lines for tests and echoes them on stderr
+struct logger {
+    std::string name;
+    std::vector<std::string> lines;
+    void log(const char *level, const std::string &msg)
+    {
+        lines.push_back(std::string(level) + ": " + msg);
+        fprintf(stderr, "%s :%s: %s\n", name.c_str(), level, msg.c_str());
+    }
+};
+typedef std::shared_ptr<logger> logger_ptr;
+#define GR_LOG_INFO(lg_, msg) (lg_)->log("info", (msg))
+#define GR_LOG_WARN(lg_, msg) (lg_)->log("warning", (msg))
+#define GR_LOG_ERROR(lg_, msg) (lg_)->log("error", (msg))
 
 // stream tag (gnuradio/tags.h): absolute offset, key, value
 struct tag_t {
@@ -124,12 +140,17 @@ public:
     std::vector<pmt::pmt_t> &published(const std::string &port) { return d_ports[port]; }
 
 protected:
-    block() {}          // allows pure-virtual interface sub-classes (as in GNU Radio)
+    block() : d_logger(new logger) {}          // allows pure-virtual interface sub-classes (as in GNU Radio)
     block(const std::string &name, io_signature::sptr in, io_signature::sptr out)
-        : d_name(name), d_in(in), d_out(out)
+        : d_logger(new logger), d_name(name), d_in(in), d_out(out)
     {
+        d_logger->name = name;
     }
     thread::mutex d_setlock;
+    logger_ptr d_logger;
+
+public:
+    const std::vector<std::string> &test_log_lines() const { return d_logger->lines; }
 
 private:
     std::string d_name;

@@ -38,11 +38,23 @@ void must(int rc, bool out_of_range = false)
     throw std::runtime_error(msg);
 }
 
-// work-time failures: log and stop the block (reference: print + exit(0), GRCLBase.cpp:239-257)
-int work_failed(const char *who)
+// work-time failures: log through the block's logger and stop the block (reference: print + exit(0),
+// GRCLBase.cpp:239-257)
+int work_failed(gr::logger_ptr log, const char *who)
 {
-    fprintf(stderr, "%s: %s\n", who, clb200_last_error());
+    GR_LOG_ERROR(log, std::string(who) + ": " + clb200_last_error());
     return gr::block::WORK_DONE;
+}
+
+// setDebug of the reference factories: log the device and kernel the block was configured with (the
+// reference prints its OpenCL device and kernel source, e.g. clXEngine_impl.cc:700-703) and have the
+// library report every work() call
+void apply_debug(gr::logger_ptr log, clb200_handle h, int setDebug)
+{
+    if (!setDebug) return;
+    char buf[768];
+    if (clb200_describe(h, buf, (int)sizeof(buf)) == CLB200_OK) GR_LOG_INFO(log, std::string(buf));
+    clb200_set_debug(h, 1);
 }
 
 struct Handle {
@@ -61,6 +73,8 @@ class clMathConst_impl : public clMathConst
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     clMathConst_impl(int idataType, int dev, float fValue, int operatorType)
         : gr::sync_block("clMathConst", gr::io_signature::make(1, 1, item_size(idataType)),
                          gr::io_signature::make(1, 1, item_size(idataType)))
@@ -73,7 +87,7 @@ public:
     int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         if (clb200_mathconst_work(d.h, in[0], out[0], noutput_items) != CLB200_OK)
-            return work_failed("clMathConst");
+            return work_failed(this->d_logger, "clMathConst");
         return noutput_items;
     }
 };
@@ -84,6 +98,8 @@ class clMathOp_impl : public clMathOp
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     clMathOp_impl(int idataType, int dev, int operatorType)
         : gr::sync_block("clMathOp", gr::io_signature::make(2, 2, item_size(idataType)),
                          gr::io_signature::make(1, 1, item_size(idataType)))
@@ -95,7 +111,7 @@ public:
     {
         if (noutput_items == 0) return 0;       // clMathOp_impl.cc:367-369
         if (clb200_mathop_work(d.h, in[0], in[1], out[0], noutput_items) != CLB200_OK)
-            return work_failed("clMathOp");
+            return work_failed(this->d_logger, "clMathOp");
         return noutput_items;
     }
 };
@@ -107,6 +123,8 @@ class unary_impl : public Base
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     unary_impl(const char *name, int kind, size_t in_size, int dev, float n, float k)
         : gr::sync_block(name, gr::io_signature::make(1, 1, in_size), gr::io_signature::make(1, 1, sizeof(float)))
     {
@@ -114,7 +132,7 @@ public:
     }
     int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
-        if (clb200_unary_work(d.h, in[0], out[0], noutput_items) != CLB200_OK) return work_failed("clenabled");
+        if (clb200_unary_work(d.h, in[0], out[0], noutput_items) != CLB200_OK) return work_failed(this->d_logger, "clenabled");
         return noutput_items;
     }
 };
@@ -124,6 +142,8 @@ class clSNR_impl : public clSNR
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     clSNR_impl(int dev, float n, float k)
         : gr::sync_block("clSNR", gr::io_signature::make(2, 2, sizeof(float)), gr::io_signature::make(1, 1, sizeof(float)))
     {
@@ -132,7 +152,7 @@ public:
     int work(int n, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         if (clb200_snr_work(d.h, (const float *)in[0], (const float *)in[1], (float *)out[0], n) != CLB200_OK)
-            return work_failed("clSNR");
+            return work_failed(this->d_logger, "clSNR");
         return n;
     }
 };
@@ -142,6 +162,8 @@ class clComplexToMagPhase_impl : public clComplexToMagPhase
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     explicit clComplexToMagPhase_impl(int dev)
         : gr::sync_block("clComplexToMagPhase", gr::io_signature::make(1, 1, sizeof(gr_complex)),
                          gr::io_signature::make(2, 2, sizeof(float)))
@@ -151,7 +173,7 @@ public:
     int work(int n, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         if (clb200_c2magphase_work(d.h, in[0], (float *)out[0], (float *)out[1], n) != CLB200_OK)
-            return work_failed("clComplexToMagPhase");
+            return work_failed(this->d_logger, "clComplexToMagPhase");
         return n;
     }
 };
@@ -161,6 +183,8 @@ class clMagPhaseToComplex_impl : public clMagPhaseToComplex
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     explicit clMagPhaseToComplex_impl(int dev)
         : gr::sync_block("clMagPhaseToComplex", gr::io_signature::make(2, 2, sizeof(float)),
                          gr::io_signature::make(1, 1, sizeof(gr_complex)))
@@ -170,7 +194,7 @@ public:
     int work(int n, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         if (clb200_magphase2c_work(d.h, (const float *)in[0], (const float *)in[1], out[0], n) != CLB200_OK)
-            return work_failed("clMagPhaseToComplex");
+            return work_failed(this->d_logger, "clMagPhaseToComplex");
         return n;
     }
 };
@@ -179,6 +203,11 @@ public:
 class clFFT_impl : public clFFT
 {
     Handle d;
+
+public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
+private:
     int d_fft_size, d_num_streams;
 
 public:
@@ -200,7 +229,7 @@ public:
     int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         if (clb200_fft_work_streams(d.h, in.data(), out.data(), d_num_streams, noutput_items) != CLB200_OK)
-            return work_failed("clFFT");
+            return work_failed(this->d_logger, "clFFT");
         return noutput_items;
     }
 };
@@ -209,6 +238,11 @@ public:
 class clFilter_impl : public clFilter
 {
     Handle d;
+
+public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
+private:
     int d_nthreads;
 
 public:
@@ -240,7 +274,7 @@ public:
     {
         long n_out = 0;
         if (clb200_filter_work(d.h, in[0], (long)noutput_items * decimation(), out[0], &n_out) != CLB200_OK)
-            return work_failed("clFilter");
+            return work_failed(this->d_logger, "clFilter");
         return (int)n_out;
     }
 };
@@ -249,6 +283,11 @@ public:
 class clPolyphaseChannelizer_impl : public clPolyphaseChannelizer
 {
     Handle d;
+
+public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
+private:
     int d_ntaps, d_buf_items, d_M, d_R, d_nmap;
 
 public:
@@ -273,7 +312,7 @@ public:
     int general_work(int, gr_vector_int &, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         const long niter = d_buf_items / d_R;
-        if (clb200_pfb_work(d.h, in[0], out[0], niter) != CLB200_OK) return work_failed("clPolyphaseChannelizer");
+        if (clb200_pfb_work(d.h, in[0], out[0], niter) != CLB200_OK) return work_failed(this->d_logger, "clPolyphaseChannelizer");
         consume_each(d_buf_items);                                   // :105
         return (int)(d_nmap * niter);                                // :108
     }
@@ -283,12 +322,17 @@ public:
 class clXEngine_impl : public clXEngine
 {
     Handle d;
+
+public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
+private:
     int d_data_type, d_npol, d_num_inputs, d_num_channels, d_integration, d_pipeline;
     bool d_disable_output;
-    size_t d_sample_bytes;
-    std::vector<char> d_buf;                  // one integration, [t][station][chan][pol]
-    std::vector<gr_complex> d_matrix;
-    int d_tracker = 0, d_pipeline_count = 0;
+    static constexpr int RESULT_SLOTS = 4;
+    size_t d_nports;
+    std::vector<gr_complex> d_matrix;         // the matrix being delivered (file frame / PDU payload)
+    int d_tracker = 0;                        // time steps of the current integration consumed so far
     // file sink (lib/clXEngine_impl.cc:393-465, :1259-1277): raw cf32_le frames + JSON sidecar
     bool d_output_file;
     std::string d_file_base, d_object_name, d_filename;
@@ -366,8 +410,10 @@ public:
                                     "align with blocks coming from the SNAP.");
         must(clb200_xengine_create(dev, data_type, polarization, num_inputs, num_channels, integration, &d.h),
              num_inputs < 2);                   // std::out_of_range, clXEngine_impl.cc:106-109
-        d_sample_bytes = data_type == DTYPE_COMPLEX ? sizeof(gr_complex) : (data_type == DTYPE_BYTE ? 2 : 1);
-        d_buf.resize((size_t)clb200_xengine_input_bytes(d.h));
+        d_nports = (size_t)num_inputs * (data_type == DTYPE_PACKEDXY ? 1 : polarization);
+        // pinned double buffers, copy / compute / read-back streams, result ring (the reference's two pinned host
+        // buffers + worker thread, :304-382, :1234-1299); pipeline_integration sums on the device (:785-808)
+        must(clb200_xengine_stream_begin(d.h, pipeline_integration, RESULT_SLOTS));
         d_matrix.resize((size_t)clb200_xengine_output_items(d.h));
         message_port_register_out(pmt::mp("xcorr"));                 // :294-295
         message_port_register_out(pmt::mp("sync"));
@@ -383,6 +429,10 @@ public:
     }
     bool stop() override
     {
+        {   // everything handed to the GPU is delivered before the block stops (the reference joins its worker, :498-520)
+            gr::thread::scoped_lock guard(d_setlock);
+            if (d.h && !pickup(1)) GR_LOG_ERROR(this->d_logger, std::string("clXEngine: ") + clb200_last_error());
+        }
         if (d_fp) {
             fclose(d_fp);
             d_fp = nullptr;
@@ -393,11 +443,36 @@ public:
     {
         for (auto &r : req) r = noutput_items;                       // :385-390
     }
-    // work_processor (:918-1142): marshal the port vectors of each time step into the
-    // integration buffer; a full buffer is correlated and published as ("triang_matrix" . c32vector)
+    // a finished visibility matrix goes to the file sink or out as ("triang_matrix" . c32vector) (:1076-1080, :1259-1277)
+    void deliver()
+    {
+        if (d_output_file) write_frame();
+        else if (!d_disable_output)
+            message_port_pub(pmt::mp("xcorr"), pmt::cons(pmt::string_to_symbol("triang_matrix"),
+                                                         pmt::init_c32vector(d_matrix.size(), d_matrix.data())));
+    }
+    // pick up whatever the GPU has finished; wait != 0 drains everything in flight
+    bool pickup(int wait)
+    {
+        for (;;) {
+            int ready = 0;
+            if (clb200_xengine_poll_result(d.h, d_matrix.data(), wait, &ready) != CLB200_OK) return false;
+            if (!ready) return true;
+            deliver();
+        }
+    }
+
+public:
+    // work_processor (:918-1142) + runThread (:1234-1299).  The reference marshals each call into one of two pinned
+    // host buffers and a worker thread uploads + correlates a full buffer; the finished matrix is published when the
+    // NEXT integration completes.  Here each call's time steps go to the device at once (clb200_xengine_push_timesteps:
+    // pinned staging + copy stream), the correlation and the read-back of a full integration are enqueued without
+    // waiting, and finished matrices are picked up on the following calls (or in stop()): the scheduler thread never
+    // waits for a kernel.
     int general_work(int noutput_items, gr_vector_int &, gr_vector_const_void_star &in, gr_vector_void_star &) override
     {
         gr::thread::scoped_lock guard(d_setlock);
+        if (!pickup(0)) return work_failed(this->d_logger, "clXEngine");
         if (d_use_sync && !d_synchronized) {
             // SNAP packets carry a sequence tag on every 16-step block (t[n+1] = t[n] + 16).  Until the first
             // tag of every input is the same, drop (highest - own) items from each input and produce nothing.
@@ -423,42 +498,17 @@ public:
             d_sync_timestamp = (long)highest;                   // goes into the JSON sidecar (write_json(highest_tag))
             message_port_pub(pmt::mp("sync"), pmt::cons(pmt::intern("synctimestamp"), pmt::from_uint64(highest)));
         }
-        int n = std::min(noutput_items, d_integration - d_tracker);
-        const size_t vec = (size_t)d_num_channels * d_sample_bytes;          // bytes of one port item
-        const size_t row = vec * d_npol;                                      // one station, one time step
-        const size_t frame = row * d_num_inputs;
-        for (int t = 0; t < n; t++) {
-            char *dst = d_buf.data() + (size_t)(d_tracker + t) * frame;
-            for (int s = 0; s < d_num_inputs; s++) {
-                if (d_npol == 1 || d_data_type == DTYPE_PACKEDXY) {
-                    memcpy(dst + s * row, (const char *)in[s] + (size_t)t * row, row);
-                } else {                                                      // interleave X,Y per channel (:1010-1057)
-                    const char *x = (const char *)in[s] + (size_t)t * vec;
-                    const char *y = (const char *)in[s + d_num_inputs] + (size_t)t * vec;
-                    char *o = dst + s * row;
-                    for (int c = 0; c < d_num_channels; c++) {
-                        memcpy(o + (2 * c) * d_sample_bytes, x + c * d_sample_bytes, d_sample_bytes);
-                        memcpy(o + (2 * c + 1) * d_sample_bytes, y + c * d_sample_bytes, d_sample_bytes);
-                    }
-                }
-            }
+        const int n = std::min(noutput_items, d_integration - d_tracker);      // :924-933: never past the integration
+        if (d_tracker + n == d_integration) {
+            // this call completes an integration: keep the result ring from filling up (the reference holds the
+            // scheduler on d_thread_active_lock here when its worker is still busy, :935-947)
+            long pending = 0;
+            clb200_xengine_stream_state(d.h, nullptr, nullptr, &pending, nullptr, nullptr);
+            if (pending >= RESULT_SLOTS - 1 && !pickup(1)) return work_failed(this->d_logger, "clXEngine");
         }
-        d_tracker += n;
-        if (d_tracker == d_integration) {
-            const bool accumulate = d_pipeline > 1 && d_pipeline_count > 0;   // :785-808
-            if (clb200_xengine_work(d.h, d_buf.data(), d_matrix.data(), accumulate ? 1 : 0) != CLB200_OK)
-                return work_failed("clXEngine");
-            d_tracker = 0;
-            d_pipeline_count++;
-            if (d_pipeline < 2 || d_pipeline_count >= d_pipeline) {
-                d_pipeline_count = 0;
-                if (d_output_file) write_frame();                    // :1259-1277
-                else if (!d_disable_output)
-                    message_port_pub(pmt::mp("xcorr"),
-                                     pmt::cons(pmt::string_to_symbol("triang_matrix"),
-                                               pmt::init_c32vector(d_matrix.size(), d_matrix.data())));   // :1076-1080
-            }
-        }
+        if (clb200_xengine_push_timesteps(d.h, in.data(), (int)d_nports, n) != CLB200_OK)
+            return work_failed(this->d_logger, "clXEngine");
+        d_tracker = (d_tracker + n) % d_integration;
         for (size_t p = 0; p < in.size(); p++) consume((int)p, n);            // :1228-1231
         return n;
     }
@@ -469,6 +519,11 @@ public:
 class clXCorrelate_impl : public clXCorrelate
 {
     Handle d;
+
+public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
+private:
     int d_num_inputs, d_signal_length, d_decim_frames, d_frame = 1;
     std::vector<float> d_corr;
     std::vector<int32_t> d_lag;
@@ -495,7 +550,7 @@ public:
             else return d_signal_length;
         }
         if (clb200_xcorrelate_work(d.h, in.data(), d_corr.data(), d_lag.data()) != CLB200_OK)
-            return work_failed("clXCorrelate");
+            return work_failed(this->d_logger, "clXCorrelate");
         pmt::pmt_t meta = pmt::make_dict();                                                       // :1585-1593
         meta = pmt::dict_add(meta, pmt::mp("corrvect"), pmt::init_f32vector(d_corr.size(), d_corr.data()));
         meta = pmt::dict_add(meta, pmt::mp("corrective_lags"), pmt::init_s32vector(d_lag.size(), d_lag.data()));
@@ -511,6 +566,8 @@ class clxcorrelate_fft_vcf_impl : public clxcorrelate_fft_vcf
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     clxcorrelate_fft_vcf_impl(int dev, int fftSize, int num_inputs, int input_type)
         : gr::sync_block("clxcorrelate_fft_vcf", gr::io_signature::make(2, num_inputs, sizeof(gr_complex) * fftSize),
                          gr::io_signature::make(1, num_inputs - 1, sizeof(float) * fftSize))
@@ -520,7 +577,7 @@ public:
     int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         if (clb200_xcorr_fft_work(d.h, in.data(), out.data(), noutput_items) != CLB200_OK)
-            return work_failed("clxcorrelate_fft_vcf");
+            return work_failed(this->d_logger, "clxcorrelate_fft_vcf");
         return noutput_items;
     }
 };
@@ -531,6 +588,8 @@ class clComplexFilter_impl : public clComplexFilter
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     clComplexFilter_impl(int dev, int decimation, const std::vector<gr_complex> &taps)
         : gr::sync_decimator("clComplexFilter", gr::io_signature::make(1, 1, sizeof(gr_complex)),
                              gr::io_signature::make(1, 1, sizeof(gr_complex)), decimation)
@@ -547,7 +606,7 @@ public:
     {
         long n_out = 0;
         if (clb200_cfilter_work(d.h, in[0], (long)noutput_items * decimation(), out[0], &n_out) != CLB200_OK)
-            return work_failed("clComplexFilter");
+            return work_failed(this->d_logger, "clComplexFilter");
         return (int)n_out;
     }
 };
@@ -558,6 +617,8 @@ class clQuadratureDemod_impl : public clQuadratureDemod
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     clQuadratureDemod_impl(int dev, float gain)
         : gr::sync_block("clQuadratureDemod", gr::io_signature::make(1, 1, sizeof(gr_complex)),
                          gr::io_signature::make(1, 1, sizeof(float)))
@@ -568,7 +629,7 @@ public:
     int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         if (clb200_quaddemod_work(d.h, in[0], out[0], noutput_items) != CLB200_OK)
-            return work_failed("clQuadratureDemod");
+            return work_failed(this->d_logger, "clQuadratureDemod");
         return noutput_items;
     }
 };
@@ -579,6 +640,8 @@ class clSignalSource_impl : public clSignalSource
     Handle d;
 
 public:
+    void enable_debug(int v) { apply_debug(this->d_logger, d.h, v); }
+
     clSignalSource_impl(int dev, int idataType, double samp_rate, int waveform, double freq, float amplitude)
         : gr::sync_block("clSignalSource", gr::io_signature::make(0, 0, 0),
                          gr::io_signature::make(1, 1, item_size(idataType)))
@@ -587,7 +650,7 @@ public:
     }
     int work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &out) override
     {
-        if (clb200_sigsource_work(d.h, out[0], noutput_items) != CLB200_OK) return work_failed("clSignalSource");
+        if (clb200_sigsource_work(d.h, out[0], noutput_items) != CLB200_OK) return work_failed(this->d_logger, "clSignalSource");
         return noutput_items;
     }
 };
@@ -595,100 +658,111 @@ public:
 } // namespace
 
 // ---------------------------------------------------------------- factories --
+template <class Impl>
+std::shared_ptr<Impl> finish(Impl *p, int setDebug)
+{
+    p->enable_debug(setDebug);
+    return gnuradio::get_initial_sptr(p);
+}
+
 clMathConst::sptr clMathConst::make(int idataType, int plat, int sel, int pid, int did, float fValue,
-                                    int operatorType, int)
+                                    int operatorType, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clMathConst_impl(idataType, pick_device(plat, sel, pid, did), fValue, operatorType));
+    return finish(new clMathConst_impl(idataType, pick_device(plat, sel, pid, did), fValue, operatorType), setDebug);
 }
-clMathOp::sptr clMathOp::make(int idataType, int plat, int sel, int pid, int did, int operatorType, int)
+clMathOp::sptr clMathOp::make(int idataType, int plat, int sel, int pid, int did, int operatorType, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clMathOp_impl(idataType, pick_device(plat, sel, pid, did), operatorType));
+    return finish(new clMathOp_impl(idataType, pick_device(plat, sel, pid, did), operatorType), setDebug);
 }
-clLog::sptr clLog::make(int plat, int sel, int pid, int did, float n, float k, int)
+clLog::sptr clLog::make(int plat, int sel, int pid, int did, float n, float k, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new unary_impl<clLog>("clLog", CLB200_UNARY_LOG10, sizeof(float),
-                                                            pick_device(plat, sel, pid, did), n, k));
+    return finish(new unary_impl<clLog>("clLog", CLB200_UNARY_LOG10, sizeof(float), pick_device(plat, sel, pid, did), n, k),
+                  setDebug);
 }
-clSNR::sptr clSNR::make(int plat, int sel, int pid, int did, float n, float k, int)
+clSNR::sptr clSNR::make(int plat, int sel, int pid, int did, float n, float k, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clSNR_impl(pick_device(plat, sel, pid, did), n, k));
+    return finish(new clSNR_impl(pick_device(plat, sel, pid, did), n, k), setDebug);
 }
-clComplexToMag::sptr clComplexToMag::make(int plat, int sel, int pid, int did, int)
+clComplexToMag::sptr clComplexToMag::make(int plat, int sel, int pid, int did, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new unary_impl<clComplexToMag>("clComplexToMag", CLB200_UNARY_COMPLEX_TO_MAG,
-                                                                     sizeof(gr_complex), pick_device(plat, sel, pid, did), 0, 0));
+    return finish(new unary_impl<clComplexToMag>("clComplexToMag", CLB200_UNARY_COMPLEX_TO_MAG, sizeof(gr_complex),
+                                                 pick_device(plat, sel, pid, did), 0, 0),
+                  setDebug);
 }
-clComplexToArg::sptr clComplexToArg::make(int plat, int sel, int pid, int did, int)
+clComplexToArg::sptr clComplexToArg::make(int plat, int sel, int pid, int did, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new unary_impl<clComplexToArg>("clComplexToArg", CLB200_UNARY_COMPLEX_TO_ARG,
-                                                                     sizeof(gr_complex), pick_device(plat, sel, pid, did), 0, 0));
+    return finish(new unary_impl<clComplexToArg>("clComplexToArg", CLB200_UNARY_COMPLEX_TO_ARG, sizeof(gr_complex),
+                                                 pick_device(plat, sel, pid, did), 0, 0),
+                  setDebug);
 }
-clComplexToMagPhase::sptr clComplexToMagPhase::make(int plat, int sel, int pid, int did, int)
+clComplexToMagPhase::sptr clComplexToMagPhase::make(int plat, int sel, int pid, int did, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clComplexToMagPhase_impl(pick_device(plat, sel, pid, did)));
+    return finish(new clComplexToMagPhase_impl(pick_device(plat, sel, pid, did)), setDebug);
 }
-clMagPhaseToComplex::sptr clMagPhaseToComplex::make(int plat, int sel, int pid, int did, int)
+clMagPhaseToComplex::sptr clMagPhaseToComplex::make(int plat, int sel, int pid, int did, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clMagPhaseToComplex_impl(pick_device(plat, sel, pid, did)));
+    return finish(new clMagPhaseToComplex_impl(pick_device(plat, sel, pid, did)), setDebug);
 }
 clFFT::sptr clFFT::make(int fftSize, int dir, const std::vector<float> &window, int idataType, int plat, int sel,
-                        int pid, int did, int, int num_streams, bool shift)
+                        int pid, int did, int setDebug, int num_streams, bool shift)
 {
-    return gnuradio::get_initial_sptr(
-        new clFFT_impl(fftSize, dir, window, idataType, pick_device(plat, sel, pid, did), num_streams, shift));
+    return finish(new clFFT_impl(fftSize, dir, window, idataType, pick_device(plat, sel, pid, did), num_streams, shift),
+                  setDebug);
 }
 clFilter::sptr clFilter::make(int plat, int sel, int pid, int did, int decimation, const std::vector<float> &taps,
-                              int nthreads, int, bool use_time)
+                              int nthreads, int setDebug, bool use_time)
 {
-    return gnuradio::get_initial_sptr(new clFilter_impl(pick_device(plat, sel, pid, did), decimation, taps, nthreads, use_time));
+    return finish(new clFilter_impl(pick_device(plat, sel, pid, did), decimation, taps, nthreads, use_time), setDebug);
 }
 clPolyphaseChannelizer::sptr clPolyphaseChannelizer::make(int plat, int sel, int pid, int did,
                                                           const std::vector<float> &taps, int buf_items,
                                                           int num_channels, int ninputs_per_iter,
-                                                          const std::vector<int> &ch_map, int)
+                                                          const std::vector<int> &ch_map, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clPolyphaseChannelizer_impl(pick_device(plat, sel, pid, did), taps, buf_items,
-                                                                      num_channels, ninputs_per_iter, ch_map));
+    return finish(new clPolyphaseChannelizer_impl(pick_device(plat, sel, pid, did), taps, buf_items, num_channels,
+                                                  ninputs_per_iter, ch_map),
+                  setDebug);
 }
-clXEngine::sptr clXEngine::make(int plat, int sel, int pid, int did, bool, int data_type, int polarization,
+clXEngine::sptr clXEngine::make(int plat, int sel, int pid, int did, bool setDebug, int data_type, int polarization,
                                 int num_inputs, int, int first_channel, int num_channels, int integration,
                                 std::vector<std::string> antenna_list, bool output_file, std::string file_base,
                                 int rollover_size_mb, bool internal_synchronizer, long sync_timestamp, std::string object_name,
                                 double starting_chan_center_freq, double channel_width, bool disable_output,
                                 int pipeline_integration)
 {
-    return gnuradio::get_initial_sptr(new clXEngine_impl(
-        pick_device(plat, sel, pid, did), data_type, polarization, num_inputs, num_channels, integration,
-        disable_output, pipeline_integration, output_file, file_base, rollover_size_mb, antenna_list, sync_timestamp,
-        object_name, first_channel, starting_chan_center_freq, channel_width, internal_synchronizer));
+    return finish(new clXEngine_impl(pick_device(plat, sel, pid, did), data_type, polarization, num_inputs, num_channels,
+                                     integration, disable_output, pipeline_integration, output_file, file_base,
+                                     rollover_size_mb, antenna_list, sync_timestamp, object_name, first_channel,
+                                     starting_chan_center_freq, channel_width, internal_synchronizer),
+                  setDebug ? 1 : 0);
 }
 
-clXCorrelate::sptr clXCorrelate::make(int plat, int sel, int pid, int did, bool, int num_inputs, int signal_length,
+clXCorrelate::sptr clXCorrelate::make(int plat, int sel, int pid, int did, bool setDebug, int num_inputs, int signal_length,
                                       int data_type, int data_size, int max_search_index, int decim_frames, bool)
 {
-    return gnuradio::get_initial_sptr(new clXCorrelate_impl(pick_device(plat, sel, pid, did), num_inputs, signal_length,
-                                                            data_type, data_size, max_search_index, decim_frames));
+    return finish(new clXCorrelate_impl(pick_device(plat, sel, pid, did), num_inputs, signal_length, data_type, data_size,
+                                        max_search_index, decim_frames),
+                  setDebug ? 1 : 0);
 }
 clxcorrelate_fft_vcf::sptr clxcorrelate_fft_vcf::make(int fftSize, int num_inputs, int plat, int sel, int pid, int did,
                                                       int input_type)
 {
-    return gnuradio::get_initial_sptr(
-        new clxcorrelate_fft_vcf_impl(pick_device(plat, sel, pid, did), fftSize, num_inputs, input_type));
+    return finish(new clxcorrelate_fft_vcf_impl(pick_device(plat, sel, pid, did), fftSize, num_inputs, input_type), 0);
 }
 clComplexFilter::sptr clComplexFilter::make(int plat, int sel, int pid, int did, int decimation,
-                                            const std::vector<gr_complex> &taps, int, int)
+                                            const std::vector<gr_complex> &taps, int, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clComplexFilter_impl(pick_device(plat, sel, pid, did), decimation, taps));
+    return finish(new clComplexFilter_impl(pick_device(plat, sel, pid, did), decimation, taps), setDebug);
 }
-clQuadratureDemod::sptr clQuadratureDemod::make(float gain, int plat, int sel, int pid, int did, int)
+clQuadratureDemod::sptr clQuadratureDemod::make(float gain, int plat, int sel, int pid, int did, int setDebug)
 {
-    return gnuradio::get_initial_sptr(new clQuadratureDemod_impl(pick_device(plat, sel, pid, did), gain));
+    return finish(new clQuadratureDemod_impl(pick_device(plat, sel, pid, did), gain), setDebug);
 }
 clSignalSource::sptr clSignalSource::make(int idataType, int plat, int sel, int pid, int did, double samp_rate,
-                                          int waveform, double freq, float amplitude, int)
+                                          int waveform, double freq, float amplitude, int setDebug)
 {
-    return gnuradio::get_initial_sptr(
-        new clSignalSource_impl(pick_device(plat, sel, pid, did), idataType, samp_rate, waveform, freq, amplitude));
+    return finish(new clSignalSource_impl(pick_device(plat, sel, pid, did), idataType, samp_rate, waveform, freq, amplitude),
+                  setDebug);
 }
 
 } // namespace clenabled

@@ -137,6 +137,9 @@ int main()
         gr_vector_const_void_star iv2;
         for (auto &p : ports) iv2.push_back(p.data() + 40 * F * 2);
         CHECK(blk->general_work(1000, ni, iv2, ov) == 24);       // only what completes the integration
+        // the correlation and its read-back run asynchronously; the matrix is published by a later call or by stop()
+        // (the reference publishes it when the next integration completes, lib/clXEngine_impl.cc:1062-1090)
+        blk->stop();
         auto &msgs = blk->published("xcorr");
         CHECK(msgs.size() == 1);
         if (msgs.size() == 1) {
@@ -181,6 +184,64 @@ int main()
             CHECK(t.find("\"data_type\":\"cf32_le\"") != std::string::npos);
         }
     }
+    // --- X-engine streaming: many small general_work() calls, results picked up on later calls; pipeline_integration
+    //     sums integrations on the device; setDebug logs the kernel description through the block's logger
+    {
+        const int A = 3, F = 16, T = 32, NI = 6;
+        auto blk = clXEngine::make(GPU, FIRST, 0, 0, true, DTYPE_BYTE, 1, A, 1, 0, F, T, {});
+        CHECK(!blk->test_log_lines().empty() && blk->test_log_lines()[0].find("clXEngine 3 inputs") != std::string::npos);
+        auto pip = clXEngine::make(GPU, FIRST, 0, 0, false, DTYPE_BYTE, 1, A, 1, 0, F, T, {}, false, "", 0, false, 0, "", 0.0,
+                                   0.0, false, 3);
+        std::vector<std::vector<signed char>> ports(A, std::vector<signed char>((size_t)NI * T * F * 2));
+        unsigned seed = 7;
+        for (auto &p : ports)
+            for (auto &v : p) {
+                seed = seed * 1664525u + 1013904223u;
+                v = (signed char)((int)(seed >> 24) % 60 - 30);
+            }
+        gr_vector_void_star ov;
+        gr_vector_int ni(A, 5);
+        int pos = 0;
+        while (pos < NI * T) {                                    // 5 time steps per call, never past an integration
+            gr_vector_const_void_star iv;
+            for (auto &p : ports) iv.push_back(p.data() + (size_t)pos * F * 2);
+            const int want = std::min(5, T - pos % T);
+            CHECK(blk->general_work(5, ni, iv, ov) == want);
+            CHECK(pip->general_work(5, ni, iv, ov) == want);
+            pos += want;
+        }
+        blk->stop();
+        pip->stop();
+        auto &msgs = blk->published("xcorr");
+        auto &pm = pip->published("xcorr");
+        CHECK((int)msgs.size() == NI);
+        CHECK((int)pm.size() == NI / 3);
+        const int nbl = A * (A + 1) / 2;
+        for (int k = 0; k < (int)msgs.size(); k++) {
+            const auto &m = pmt::c32vector_elements(pmt::cdr(msgs[k]));
+            // baseline (1,0) of channel 2 by direct summation: V = sum_t x1 conj(x0) / 127^2
+            double re = 0, im = 0;
+            for (int t = 0; t < T; t++) {
+                const size_t o = ((size_t)(k * T + t) * F + 2) * 2;
+                const double ar = ports[1][o], ai = ports[1][o + 1], br = ports[0][o], bi = ports[0][o + 1];
+                re += ar * br + ai * bi;
+                im += ai * br - ar * bi;
+            }
+            const gr_complex v = m[(size_t)2 * nbl + 1];
+            CHECK(std::abs(v.real() - re / 16129.0) < 1e-3 && std::abs(v.imag() - im / 16129.0) < 1e-3);
+        }
+        if ((int)msgs.size() == NI && (int)pm.size() == NI / 3)
+            for (int g = 0; g < NI / 3; g++) {                    // a pipelined matrix = the sum of its three integrations
+                const auto &s = pmt::c32vector_elements(pmt::cdr(pm[g]));
+                double worst = 0;
+                for (size_t i = 0; i < s.size(); i++) {
+                    gr_complex acc(0, 0);
+                    for (int j = 0; j < 3; j++) acc += pmt::c32vector_elements(pmt::cdr(msgs[3 * g + j]))[i];
+                    worst = std::max(worst, (double)std::abs(acc - s[i]));
+                }
+                CHECK(worst < 1e-3);
+            }
+    }
     // --- clXEngine ATA synchroniser (lib/clXEngine_impl.cc:1158-1226): inputs whose first SNAP sequence tags differ
     //     are trimmed to the highest tag; once equal, "synctimestamp" is published and data flows
     {
@@ -202,6 +263,7 @@ int main()
         CHECK(blk->general_work(T, ni, iv, ov) == T);
         CHECK(blk->published("sync").size() == 1);
         if (!blk->published("sync").empty()) CHECK(pmt::to_uint64(pmt::cdr(blk->published("sync")[0])) == 1016);
+        blk->stop();
         CHECK(blk->published("xcorr").size() == 1);
     }
     // --- clXCorrelate: a copy delayed by 5 samples -> corrective lag -5, published on port "corr"

@@ -90,6 +90,12 @@ CLB200_API int clb200_destroy(clb200_handle h);           /* any handle; GRCLBas
 /* counters since creation: bytes H2D, bytes D2H, kernel launches */
 CLB200_API int clb200_get_counters(clb200_handle h, uint64_t *h2d, uint64_t *d2h, uint64_t *launches);
 
+/* setDebug of the reference factories (GR_LOG_INFO of the device and kernel, e.g. lib/clXEngine_impl.cc:700-703):
+ * describe() gives the kernel variant and launch geometry the handle was configured with; set_debug(1)
+ * makes the host path print one line per work() call (items, chunks, microseconds) on stderr.           */
+CLB200_API int clb200_describe(clb200_handle h, char *buf, int buflen);
+CLB200_API int clb200_set_debug(clb200_handle h, int on);
+
 /* Optional: page-lock a caller-owned host range (e.g. a GNU Radio circular buffer,
  * once, in start()) so that work() calls on it skip the staging copy and are DMA'd /
  * read by the kernels in place.  The range must stay valid until unregistered.   */
@@ -214,6 +220,28 @@ CLB200_API int clb200_xengine_launch_device(clb200_handle h, const void *d_in, v
                                             int accumulate, void *stream);
 CLB200_API int clb200_xengine_launch_device_i32(clb200_handle h, const void *d_in,
                                                 int32_t *d_out_i32, void *stream);
+/* Streaming ingest -- the shape of the reference block: work_processor (lib/clXEngine_impl.cc:918-1142) marshals
+ * each general_work() call's port vectors into a pinned integration buffer, and a worker (runThread
+ * :1234-1299) uploads and correlates a full buffer while the next one fills.  Here:
+ *   stream_begin   allocates two pinned + two device integration buffers, a ring of result matrices and
+ *                  the copy / compute / read-back streams.  pipeline_integration > 1 sums that many
+ *                  integrations on the device before a result is emitted (:785-808, :1249-1284).
+ *   push_timesteps `ntime` time steps: ports[s] -> ntime items of station s (item = the caller's channels,
+ *                  this handle's slab of them after set_shard); unpacked two-polarisation data comes as
+ *                  2*num_inputs ports (X = ports[s], Y = ports[s + num_inputs]) and is interleaved per channel
+ *                  (:1010-1057).  Every push is uploaded AT ONCE on the copy stream; a completed integration
+ *                  is correlated and its matrix read back asynchronously.  The call only waits for the GPU
+ *                  when it is a whole integration behind.  The ports may be reused on return.  Page-locked
+ *                  ports (clb200_register_host_buffer) of >= 1 MiB per push are DMA'd in place.
+ *   poll_result    copies the oldest finished matrix into out_c32 (*ready = 1) or reports *ready = 0;
+ *                  wait != 0 blocks until it is there.  At most result_slots matrices may be pending.
+ *   stream_end     drains and frees the stream state (also done by clb200_destroy).                        */
+CLB200_API int clb200_xengine_stream_begin(clb200_handle h, int pipeline_integration, int result_slots);
+CLB200_API int clb200_xengine_push_timesteps(clb200_handle h, const void *const *ports, int nports, long ntime);
+CLB200_API int clb200_xengine_poll_result(clb200_handle h, void *out_c32, int wait, int *ready);
+CLB200_API int clb200_xengine_stream_state(clb200_handle h, long *tracker, long *integrations, long *results_pending,
+                                           uint64_t *pushes, uint64_t *pushes_blocked);
+CLB200_API int clb200_xengine_stream_end(clb200_handle h);
 /* channel-sharded variant for multi-GPU: this handle owns channels
  * [chan_first, chan_first+chan_count) of an integration whose host layout has
  * total_channels per station; work() gathers only that slab (cudaMemcpy2D).      */

@@ -411,6 +411,118 @@ def test_xengine_channel_shard_matches_full():
     assert np.array_equal(np.concatenate(parts, axis=0), full)
 
 
+def _ports_of(buf, T, A, F, npol, sb, planar):
+    """the block's input streams for an integration buffer [t][station][chan][pol](sample): one array per station
+    (per station and polarisation for unpacked two-polarisation data), each [t][chan]"""
+    b = np.ascontiguousarray(buf).view(np.uint8).reshape(T, A, F, npol, sb)
+    if planar:
+        return [np.ascontiguousarray(b[:, s, :, p, :]).reshape(-1) for p in range(npol) for s in range(A)]
+    return [np.ascontiguousarray(b[:, s]).reshape(-1) for s in range(A)]
+
+
+@pytest.mark.parametrize("dtype,npol,A,F,T", [
+    ("byte", 1, 8, 32, 96), ("byte", 2, 5, 16, 64), ("complex", 1, 4, 12, 40), ("complex", 2, 3, 8, 33),
+    ("packed", 2, 6, 16, 64), ("byte", 1, 32, 64, 256),
+])
+def test_xengine_streaming_push_poll_matches_oracle(dtype, npol, A, F, T):
+    """clb200_xengine_stream_begin / push_timesteps / poll_result (the general_work shape of the reference block,
+    lib/clXEngine_impl.cc:918-1142, 1234-1299): ragged pushes that cross integration boundaries, results picked
+    up later, every matrix equal to the whole-buffer call and to the oracle"""
+    NI = 5
+    dt = {"byte": capi.DTYPE_BYTE, "complex": capi.DTYPE_COMPLEX, "packed": capi.DTYPE_PACKEDXY}[dtype]
+    sb = {"byte": 2, "complex": 8, "packed": 1}[dtype]
+    planar = npol == 2 and dtype != "packed"
+    per = T * A * F * npol
+    if dtype == "byte":
+        bufs = [orc.rng_i8(per * 2, orc.SEED_X + 20 + i) for i in range(NI)]
+    elif dtype == "complex":
+        bufs = [orc.rng_c32(per, orc.SEED_X + 20 + i) for i in range(NI)]
+    else:
+        bufs = [orc.rng_i8(per, orc.SEED_X + 20 + i).view(np.uint8) for i in range(NI)]
+    whole = _xe(dt, npol, A, F, T)
+    want = [whole.work(b) for b in bufs]
+    if dtype == "byte":
+        assert rel_err(want[0], orc.xengine_f32(bufs[0], A, F, T, npol)) < TOL
+    # the stream: all integrations back to back, per port
+    per_int = [_ports_of(b, T, A, F, npol, sb, planar) for b in bufs]
+    ports = [np.concatenate([pi[k] for pi in per_int]) for k in range(len(per_int[0]))]
+    item = F * sb * (1 if planar else npol)
+    blk = _xe(dt, npol, A, F, T)
+    blk.stream_begin(0, 8)
+    got, pos, cuts = [], 0, [1, 7, T - 3, 2 * T + 5, 3, T, 9999]
+    for c in cuts:
+        n = min(c, NI * T - pos)
+        if n <= 0:
+            break
+        blk.push([p[pos * item:] for p in ports], n)
+        pos += n
+        while True:
+            m = blk.poll(wait=False)
+            if m is None:
+                break
+            got.append(m)
+    while len(got) < NI:
+        m = blk.poll(wait=True)
+        assert m is not None
+        got.append(m)
+    assert blk.poll(wait=True) is None
+    st = blk.stream_state()
+    assert st["integrations"] == NI and st["tracker"] == 0 and st["results_pending"] == 0
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w) if dtype != "complex" else rel_err(g, w) < 1e-6
+    blk.stream_end()
+
+
+def test_xengine_streaming_pipeline_shard_pinned_ports_and_backpressure():
+    A, F, T = 8, 64, 128
+    NI = 4
+    bufs = [orc.rng_i8(T * A * F * 2, orc.SEED_X + 40 + i) for i in range(NI)]
+    whole = _xe(capi.DTYPE_BYTE, 1, A, F, T)
+    want = [whole.work(b) for b in bufs]
+    ports = [np.concatenate([_ports_of(b, T, A, F, 1, 2, False)[s] for b in bufs]) for s in range(A)]
+    # pipeline_integration = 2: one matrix per two integrations, summed on the device (:785-808)
+    blk = _xe(capi.DTYPE_BYTE, 1, A, F, T)
+    blk.stream_begin(2, 2)
+    blk.push(ports, NI * T)
+    m0, m1 = blk.poll(wait=True), blk.poll(wait=True)
+    assert rel_err(m0, want[0] + want[1]) < 1e-6 and rel_err(m1, want[2] + want[3]) < 1e-6
+    # back-pressure: a full result ring refuses the push and changes nothing
+    blk.push(ports, NI * T)
+    with pytest.raises(capi.Clb200Error) as ei:
+        blk.push(ports, T)
+    assert ei.value.code == capi.ESTATE
+    assert blk.stream_state()["results_pending"] == 2
+    assert rel_err(blk.poll(wait=True), want[0] + want[1]) < 1e-6
+    # channel shard of a wider stream (set_shard) + page-locked ports (DMA'd in place for pushes >= 1 MiB)
+    lib = capi.load()
+    A2, F2, T2 = 16, 256, 256
+    big = orc.rng_i8(T2 * A2 * F2 * 2, orc.SEED_X + 50)
+    full = _xe(capi.DTYPE_BYTE, 1, A2, F2, T2).work(big).reshape(F2, -1)
+    pports = _ports_of(big, T2, A2, F2, 1, 2, False)
+    for p in pports:
+        capi.check(lib.clb200_register_host_buffer(C.c_void_p(p.ctypes.data), p.nbytes))
+    try:
+        for first in (0, 128):
+            sh = _xe(capi.DTYPE_BYTE, 1, A2, 128, T2)
+            sh.set_shard(F2, first)
+            sh.stream_begin(0, 2)
+            sh.push(pports, T2)
+            assert np.array_equal(sh.poll(wait=True).reshape(128, -1), full[first:first + 128])
+    finally:
+        for p in pports:
+            lib.clb200_unregister_host_buffer(C.c_void_p(p.ctypes.data))
+
+
+def test_describe_and_set_debug(capfd):
+    blk = blocks.clFFT(8192, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU)
+    buf = C.create_string_buffer(512)
+    capi.check(capi.load().clb200_describe(blk._h, buf, 512))
+    assert b"clFFT 8192-pt forward" in buf.value and b"k_fft<13," in buf.value
+    capi.check(capi.load().clb200_set_debug(blk._h, 1))
+    blk.work(orc.rng_c32(8192, 1))
+    assert "clenabled_b200[debug]" in capfd.readouterr().err
+
+
 def test_xengine_baseline_config_properties():
     """BASELINE config 5 (32 stations x 1024 channels, integration 1024, IChar): the oracle checks
     a 16-channel slab exactly; the whole result is checked through Hermitian/real-diagonal
