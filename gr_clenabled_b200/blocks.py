@@ -388,6 +388,9 @@ class clXEngine(_Block):
     def launch_device(self, d_in, d_out, accumulate=False, stream=0):
         check(self._lib.clb200_xengine_launch_device(self._h, d_in, d_out, int(accumulate), stream))
 
+    def launch_device_batch(self, d_in, d_out, nbatch, stream=0):
+        check(self._lib.clb200_xengine_launch_device_batch(self._h, d_in, d_out, int(nbatch), stream))
+
     def launch_device_i32(self, d_in, d_out, stream=0):
         check(self._lib.clb200_xengine_launch_device_i32(self._h, d_in, d_out, stream))
 
@@ -397,6 +400,13 @@ class clXEngine(_Block):
 
     def launch_device_gather(self, d_in, stream=0):
         check(self._lib.clb200_xengine_launch_device_gather(self._h, d_in, stream))
+
+    def set_gather_sync(self, my_rank, flag_ptrs, multicast_out=None, multicast_flags=None):
+        a = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        check(self._lib.clb200_xengine_set_gather_sync(self._h, int(my_rank), a, multicast_out, multicast_flags))
+
+    def gather_wait(self, stream=0):
+        check(self._lib.clb200_xengine_gather_wait(self._h, stream))
 
 
 # ------------------------------------------------------------------------------------------

@@ -11,7 +11,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libclenabled_b200.so")
+# CLB200_LIB_PATH: an alternative build of the same library (kernel A/B measurements in tools/)
+LIB_PATH = os.environ.get("CLB200_LIB_PATH") or os.path.join(_HERE, "lib", "libclenabled_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "clenabled_b200.h")
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
@@ -91,6 +92,7 @@ SIGNATURES = {
     "clb200_xengine_work_i32": (_i, [_vp, _vp, _vp]),
     "clb200_xengine_launch_device": (_i, [_vp, _vp, _vp, _i, _vp]),
     "clb200_xengine_launch_device_i32": (_i, [_vp, _vp, _vp, _vp]),
+    "clb200_xengine_launch_device_batch": (_i, [_vp, _vp, _vp, _i, _vp]),
     "clb200_xengine_stream_begin": (_i, [_vp, _i, _i]),
     "clb200_xengine_push_timesteps": (_i, [_vp, _ph, _i, _l]),
     "clb200_xengine_poll_result": (_i, [_vp, _vp, _i, _pi]),
@@ -99,6 +101,8 @@ SIGNATURES = {
     "clb200_xengine_set_shard": (_i, [_vp, _i, _i]),
     "clb200_xengine_set_gather": (_i, [_vp, _i, _ph]),
     "clb200_xengine_launch_device_gather": (_i, [_vp, _vp, _vp]),
+    "clb200_xengine_set_gather_sync": (_i, [_vp, _i, _ph, _vp, _vp]),
+    "clb200_xengine_gather_wait": (_i, [_vp, _vp]),
     "clb200_mem_alloc": (_i, [_i, C.c_size_t, _ph]),
     "clb200_mem_free": (_i, [_i, _vp]),
     "clb200_mem_copy_to_host": (_i, [_i, _vp, _vp, C.c_size_t]),

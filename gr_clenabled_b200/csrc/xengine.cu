@@ -54,6 +54,8 @@ struct XeParams {
     int accumulate;         // out += result
     int split;              // CTAs share channel groups: partial sums meet through int32 atomics
     int nslice;             // > 0: time-sliced decomposition, grid = groups x nslice
+    int nbatch;             // integrations back to back in `in` (and matrices in `out`), one grid (TMA kernel, nslice > 0)
+    int dbg;                // timing experiments only (CLB200_XE_DBG): 1 = skip the write-out, 2 = skip the TMEM drain
     int l2_rows;            // prefetch whole (t, station) rows into L2 ahead of the demand loads
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
@@ -62,6 +64,14 @@ struct XeParams {
     float2 *gather[8];
     int ngather;
     long gather_off;
+    // ... the result may instead leave through ONE NVSwitch multicast store per 16 B (gather_mc: multicast address of
+    // the full matrix, mapped on every rank), and the completion of this rank's slab is announced to every rank by a
+    // release store of `gather_epoch` into flag slot [my rank] of their flag arrays once the LAST CTA has stored
+    float2 *gather_mc;
+    unsigned *gather_flag[8];       // per destination rank: address of ITS flag word for this source rank (or null)
+    unsigned *gather_flag_mc;       // multicast address of the flag word for this source rank (or null)
+    unsigned *gather_counter;       // CTAs of this launch that have finished their stores
+    unsigned gather_epoch;
 };
 
 // which row tiles warp share Q of WPC owns
@@ -412,6 +422,19 @@ __global__ void k_xengine_c32(const float2 *__restrict__ in, float2 *__restrict_
     }
 }
 
+// consumer side of the fused gather: lane r acquires rank r's flag until it carries `epoch` (or a later one)
+__global__ void k_gather_wait(const unsigned *flags, int nranks, unsigned epoch)
+{
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        const unsigned *f = flags + (size_t)r * CLB200_XENGINE_FLAG_STRIDE;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while ((int)(v - epoch) < 0);
+    }
+}
+
 __global__ void k_i32_to_f32(const int2 *__restrict__ in, float2 *__restrict__ out, long n,
                              float scale, int accumulate)
 {
@@ -459,6 +482,13 @@ struct XEngine : clb200_block {
     int l2promo = 0;
     void *gather[8] = {};              // full matrices of every rank (clb200_xengine_set_gather)
     int ngather = 0;
+    // completion flags of the fused gather (clb200_xengine_set_gather_sync)
+    int gather_rank = -1;
+    unsigned *gather_flags[8] = {};    // flag array of every rank (peer-mapped): word [src * FLAG_STRIDE] = epoch of src's slab
+    void *gather_mc = nullptr;         // NVSwitch multicast address of the matrix (optional)
+    unsigned *gather_flags_mc = nullptr;
+    unsigned gather_epoch = 0;
+    Buf d_gather_counter;
     int fc_override = 0;               // CLB200_XE_FC: channels per CTA of the TMA kernel (8 | 16)
     bool pdl = true;                   // programmatic dependent launch (CLB200_XE_PDL=0 turns it off)
     Buf d_in[2], d_unpacked, d_acc, d_out;
@@ -503,6 +533,7 @@ struct XEngine : clb200_block {
         d_acc.release();
         d_out.release();
         pin_out.release();
+        d_gather_counter.release();
         if (ev_done) cudaEventDestroy(ev_done);
         stream_free();
         if (s_copy) cudaStreamDestroy(s_copy);
@@ -534,7 +565,7 @@ struct XEngine : clb200_block {
 // enqueue the correlation of `T` time steps held at d_in (layout [t][A][Fstride][npol]);
 // exactly one of out_i32 / out_f32 may be null
 int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32_t *out_i32,
-              float2 *out_f32, int accumulate, cudaStream_t st, bool gather = false)
+              float2 *out_f32, int accumulate, cudaStream_t st, bool gather = false, int nbatch = 1)
 {
     const int sms = device_sm_count(x->device);
     if (x->data_type == CLB200_DTYPE_COMPLEX) {
@@ -572,6 +603,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         // two polarisations: 8 channels are already 32 B runs, and enough 8-channel groups to fill the SMs need
         // no time slicing, i.e. no exchange at all (measured 18.2 vs 20.7 us at 16 stations x 2 pols x 1024 channels)
         if (x->npol == 2 && (x->F + 7) / 8 >= sms / 2 && (x->F + 7) / 8 <= sms) fc = 8;
+        if (nbatch > 1) fc = 16;                         // persistent over (integration, group): the widest rows
         if (x->fc_override == 8 || x->fc_override == 16) fc = x->fc_override;
     }
     const int kt = tma_ok ? 512 / fc : XE_TT;           // time steps per stage
@@ -586,18 +618,28 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         if (e && ngroups < 2 * sms && nst > 1) tslices = std::min(nst, atoi(e));
     }
     if (gather && tslices == 0) tslices = 1;            // whole groups per CTA: no partial sums in memory
+    // batches: persistent CTAs over (integration, channel group) pairs, whole integrations per pair -- no time slicing,
+    // no exchange, and the pipeline runs across pair boundaries (CLB200_XE_BATCH_SLICED=1 keeps the sliced grid x K)
+    static const bool batch_sliced = [] { const char *e = getenv("CLB200_XE_BATCH_SLICED"); return e && atoi(e); }();
+    if (nbatch > 1 && tma_ok && !batch_sliced) tslices = 0;
+    else if (nbatch > 1 && tslices == 0) tslices = 1;
     if (tma_ok && tslices > 1) {
         // the slices of a group are the CTAs of one cluster: 2, 4 or 8, each finalising fc/slices channels
         int c = 2;
         while (c * 2 <= std::min(tslices, std::min(8, fc))) c *= 2;
         tslices = c;
     }
-    const bool split = (tslices > 1) || (tslices == 0 && ngroups < 2 * sms && nst > 1);
+    const bool split = (tslices > 1) || (tslices == 0 && nbatch == 1 && ngroups < 2 * sms && nst > 1);
     const int nslice = split ? 2 : 1;
-    const int grid = tslices > 0 ? ngroups * tslices
-                                 : (int)std::min<long>(sms, split ? (long)ngroups * nst : ngroups);
+    int grid = tslices > 0 ? ngroups * tslices
+                           : (int)std::min<long>(sms, split ? (long)ngroups * nst : (long)ngroups * nbatch);
+    if (nbatch > 1 && tslices == 0) {
+        static const int bg = [] { const char *e = getenv("CLB200_XE_BATCH_GRID"); return e ? atoi(e) : 0; }();   // tuning
+        if (bg > 0) grid = std::min(bg, ngroups * nbatch);
+    }
     CUtensorMap tmap;
-    const bool tma = tma_ok && tm_make_map(&tmap, src, rowb, x->A, T, x->npol, fc, x->l2promo);
+    const bool tma = tma_ok && tm_make_map(&tmap, src, rowb, x->A, T, x->npol, fc, x->l2promo, nbatch);
+    CLB_CHECK(tma || nbatch == 1, CLB200_ESTATE, "clXEngine: batched launches need the TMA kernel");
     CLB_CHECK(tma || !tma_ok, CLB200_ECUDA, "clXEngine: cuTensorMapEncodeTiled failed");
     // TMA kernel, time-sliced: the slices of a channel group form a thread-block cluster and meet
     // through distributed shared memory -- no memset, no atomics, no conversion pass
@@ -617,8 +659,11 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.out_f32 = out_f32;
     p.split = split ? 1 : 0;
     p.nslice = tslices;
+    p.nbatch = nbatch;
     {
         const char *e = getenv("CLB200_XE_L2ROWS");
+        static const int dbg = [] { const char *d = getenv("CLB200_XE_DBG"); return d ? atoi(d) : 0; }();
+        p.dbg = dbg;
         p.l2_rows = e ? atoi(e) : 0;      // measured slower on B200 (50.9 vs 44.7 us): off by default
     }
     p.A = x->A;
@@ -630,6 +675,19 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.accumulate = accumulate;
     p.ngather = 0;
     p.gather_off = 0;
+    p.gather_mc = nullptr;
+    p.gather_flag_mc = nullptr;
+    p.gather_counter = nullptr;
+    p.gather_epoch = 0;
+    for (int r = 0; r < 8; r++) p.gather_flag[r] = nullptr;
+    if (gather && x->gather_rank >= 0) {
+        p.gather_mc = (float2 *)x->gather_mc;
+        p.gather_counter = (unsigned *)x->d_gather_counter.p;
+        p.gather_epoch = ++x->gather_epoch;
+        if (x->gather_flags_mc) p.gather_flag_mc = x->gather_flags_mc + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE;
+        for (int r = 0; r < x->ngather; r++)
+            p.gather_flag[r] = x->gather_flags[r] ? x->gather_flags[r] + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE : nullptr;
+    }
     if (gather) {
         CLB_CHECK(tma, CLB200_ESTATE, "clXEngine: the peer-memory gather needs the TMA kernel (16 B aligned rows, <= 32 inputs x pols)");
         p.ngather = x->ngather;
@@ -640,7 +698,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.aligned = ((uintptr_t)src % 4 == 0) && (rowb % 4 == 0) && (((long)f_off * x->npol * 2) % 4 == 0);
     if (tma) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
+        cfg.gridDim = dim3(tslices > 0 ? grid * nbatch : grid);
         cfg.blockDim = dim3(TM_THREADS);
         cfg.dynamicSmemBytes = TM_SMEM;
         cfg.stream = st;
@@ -1053,6 +1111,40 @@ int clb200_xengine_set_gather(clb200_handle h, int nranks, void *const *full_out
     return CLB200_OK;
 }
 
+int clb200_xengine_set_gather_sync(clb200_handle h, int my_rank, void *const *flag_arrays, void *multicast_out,
+                                   void *multicast_flags)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(x->ngather > 0, CLB200_ESTATE, "clXEngine: set_gather first");
+    CLB_CHECK(my_rank >= 0 && my_rank < x->ngather && flag_arrays != nullptr, CLB200_EINVAL, "bad rank / flag arrays");
+    CLB_CHECK(((uintptr_t)multicast_out % 16) == 0, CLB200_EINVAL, "multicast address must be 16 B aligned");
+    DeviceGuard g(x->device);
+    for (int r = 0; r < x->ngather; r++) {
+        CLB_CHECK(flag_arrays[r] != nullptr, CLB200_EINVAL, "null flag array %d", r);
+        x->gather_flags[r] = (unsigned *)flag_arrays[r];
+    }
+    CLB_TRY(x->d_gather_counter.reserve(256));
+    CLB_CUDA(cudaMemset(x->d_gather_counter.p, 0, 256));
+    x->gather_rank = my_rank;
+    x->gather_mc = multicast_out;
+    x->gather_flags_mc = (unsigned *)multicast_flags;
+    x->gather_epoch = 0;
+    return CLB200_OK;
+}
+
+int clb200_xengine_gather_wait(clb200_handle h, void *stream)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(x->gather_rank >= 0, CLB200_ESTATE, "clXEngine: set_gather_sync first");
+    DeviceGuard g(x->device);
+    k_gather_wait<<<1, 32, 0, (cudaStream_t)stream>>>(x->gather_flags[x->gather_rank], x->ngather, x->gather_epoch);
+    CLB_CUDA(cudaGetLastError());
+    x->n_launch++;
+    return CLB200_OK;
+}
+
 int clb200_xengine_launch_device_gather(clb200_handle h, const void *d_in, void *stream)
 {
     XEngine *x;
@@ -1090,6 +1182,28 @@ int clb200_xengine_launch_device(clb200_handle h, const void *d_in, void *d_out_
     const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
     return xe_launch(x, d_in, x->T, Ftot, x->f_first, nullptr, (float2 *)d_out_c32, accumulate,
                      (cudaStream_t)stream);
+}
+
+int clb200_xengine_launch_device_batch(clb200_handle h, const void *d_in, void *d_out_c32, int nbatch, void *stream)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    CLB_CHECK(nbatch >= 1 && nbatch <= 4096, CLB200_EINVAL, "clXEngine: batch of %d integrations", nbatch);
+    CLB_CHECK(x->data_type == CLB200_DTYPE_BYTE, CLB200_EINVAL, "clXEngine: batched launches take IChar input");
+    DeviceGuard g(x->device);
+    const int Ftot = x->Ftotal > 0 ? x->Ftotal : x->F;
+    const size_t in_stride = (size_t)x->T * x->A * Ftot * x->npol * 2;
+    const long rowb = (long)Ftot * x->npol * 2;
+    // one grid over all integrations with the TMA kernel (one channel group, or one time slice of it, per CTA);
+    // else one launch each
+    const bool one_grid = x->use_tc && x->use_tma && ((uintptr_t)d_in % 16 == 0) && (rowb % 16 == 0) &&
+                          ((uintptr_t)d_out_c32 % 8 == 0) && nbatch > 1;
+    if (one_grid)
+        return xe_launch(x, d_in, x->T, Ftot, x->f_first, nullptr, (float2 *)d_out_c32, 0, (cudaStream_t)stream, false, nbatch);
+    for (int k = 0; k < nbatch; k++)
+        CLB_TRY(xe_launch(x, (const char *)d_in + (size_t)k * in_stride, x->T, Ftot, x->f_first, nullptr,
+                          (float2 *)d_out_c32 + (size_t)k * x->out_items(), 0, (cudaStream_t)stream));
+    return CLB200_OK;
 }
 
 int clb200_xengine_launch_device_i32(clb200_handle h, const void *d_in, int32_t *d_out_i32, void *stream)

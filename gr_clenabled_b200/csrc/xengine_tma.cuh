@@ -22,10 +22,18 @@
 
 namespace {
 
-constexpr int TM_NR = 3;                       // raw ring depth
-constexpr int TM_NI = 3;                       // image ring depth
+#ifndef CLB_TM_NR
+#define CLB_TM_NR 3
+#define CLB_TM_NI 3
+#define CLB_TM_IMGB (16 * (2048 + 64))
+#endif
+constexpr int TM_NR = CLB_TM_NR;               // raw ring depth
+constexpr int TM_NI = CLB_TM_NI;               // image ring depth
 constexpr int TM_RAWB = 32 * 1024;             // bytes per raw box: 32 t x (32 stations x 32 B | 16 x 64 B)
-constexpr int TM_IMGB = 16 * (2048 + 64);      // bytes reserved per stage image (FC channels x KT steps x 64 rows + skew)
+constexpr int TM_IMGB = CLB_TM_IMGB;           // bytes reserved per stage image (FC channels x KT steps x 64 rows + skew)
+// the image ring doubles as the epilogue's staging area: 16 channels x (544 + 4) visibilities x 8 B at most
+static_assert(TM_NI * TM_IMGB >= 16 * 548 * 8, "epilogue staging does not fit the image ring");
+static_assert(TM_NR * TM_RAWB >= 16 * 548 * 8, "cluster exchange does not fit the raw ring");
 constexpr int TM_SMEM = 1024 + TM_NR * TM_RAWB + TM_NI * TM_IMGB + 256;
 constexpr int TM_THREADS = XE_THREADS + 64;    // 16 transpose/epilogue warps + MMA warp + TMA warp
 
@@ -36,11 +44,12 @@ __device__ __forceinline__ void tm_expect_tx(uint64_t *bar, uint32_t bytes)
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void tm_load_3d(uint32_t dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2)
+// box of the 4-D map (row bytes | time | station | integration of a batch)
+__device__ __forceinline__ void tm_load_4d(uint32_t dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(tm), "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tm_ldsm_t8(uint32_t addr, uint32_t (&r)[4])
@@ -82,15 +91,91 @@ __device__ __forceinline__ void tm_mbar_wait_cluster(uint64_t *bar, uint32_t par
         : "memory");
 }
 
+// Gather write-out, 16 B at a time: pairs of visibilities (npp even, so a pair never straddles two channels and
+// both the staging and the output addresses are 16 B aligned).  One multicast store per pair when the matrices are
+// bound to an NVSwitch multicast object (the switch replicates it to every rank), else one peer store per rank.
+template <int NPOL>
+__device__ __forceinline__ void tm_write_out_gather16(const XeParams &p, const int2 *stg, const int2 *recv, int nrecv,
+                                                      int rstride, int spp, int npp, int f0, int nch, int tid)
+{
+    const float scale = p.scale;
+    const int hpp = npp >> 1, hsp = spp >> 1;                // pairs per channel in the output / in the staging
+    const int npair = nch * hpp, pad = hsp - hpp;
+    const int4 *stg4 = reinterpret_cast<const int4 *>(stg), *recv4 = reinterpret_cast<const int4 *>(recv);
+    const int rs4 = rstride >> 1;
+    const long obase = (p.gather_off + (long)f0 * npp) >> 1;  // in float4 units
+    constexpr int UN = 4;
+    int r = tid, si = tid;
+    while (r >= hpp) {
+        r -= hpp;
+        si += pad;
+    }
+    for (int i0 = tid; i0 < npair; i0 += UN * XE_THREADS) {
+        int sk[UN];
+        int4 v[UN];
+#pragma unroll
+        for (int k = 0; k < UN; k++) {
+            sk[k] = si;
+            r += XE_THREADS;
+            si += XE_THREADS;
+            while (r >= hpp) {
+                r -= hpp;
+                si += pad;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UN; k++) v[k] = (i0 + k * XE_THREADS < npair) ? stg4[sk[k]] : make_int4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int s = 0; s < nrecv; s++) {
+            int4 w[UN];
+#pragma unroll
+            for (int k = 0; k < UN; k++)
+                w[k] = (i0 + k * XE_THREADS < npair) ? recv4[s * rs4 + sk[k]] : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < UN; k++) {
+                v[k].x += w[k].x;
+                v[k].y += w[k].y;
+                v[k].z += w[k].z;
+                v[k].w += w[k].w;
+            }
+        }
+        float4 o[UN];
+#pragma unroll
+        for (int k = 0; k < UN; k++)
+            o[k] = make_float4((float)v[k].x * scale, (float)v[k].y * scale, (float)v[k].z * scale, (float)v[k].w * scale);
+        if (p.gather_mc != nullptr) {
+            float4 *dst = reinterpret_cast<float4 *>(p.gather_mc) + obase;
+#pragma unroll
+            for (int k = 0; k < UN; k++)
+                if (i0 + k * XE_THREADS < npair)
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i0 + k * XE_THREADS),
+                                 "f"(o[k].x), "f"(o[k].y), "f"(o[k].z), "f"(o[k].w)
+                                 : "memory");
+        } else {
+            for (int g = 0; g < p.ngather; g++) {
+                float4 *dst = reinterpret_cast<float4 *>(p.gather[g]) + obase;
+#pragma unroll
+                for (int k = 0; k < UN; k++)
+                    if (i0 + k * XE_THREADS < npair) dst[i0 + k * XE_THREADS] = o[k];
+            }
+        }
+    }
+}
+
 // Final visibilities of `nch` channels starting at channel f0: staged partial sums (`stg`, channel
 // stride spp) plus `nrecv` received blocks of the same shape, written in output order
 // [channel][baseline][pol^2] as int32 pairs and/or scaled floats (= or +=).
 template <int NPOL>
 __device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg, const int2 *recv, int nrecv,
-                                             int rstride, int spp, int npp, int f0, int nch, int tid)
+                                             int rstride, int spp, int npp, int f0, int nch, int tid, long kofs = 0)
 {
-    int2 *const oi = reinterpret_cast<int2 *>(p.out_i32) + (long)f0 * npp;
-    float2 *const of = p.out_f32 + (long)f0 * npp;
+    if (p.ngather > 0 && (npp & 1) == 0 && ((p.gather_off + (long)f0 * npp) & 1) == 0 && p.out_i32 == nullptr &&
+        p.out_f32 == nullptr) {
+        tm_write_out_gather16<NPOL>(p, stg, recv, nrecv, rstride, spp, npp, f0, nch, tid);
+        return;
+    }
+    int2 *const oi = reinterpret_cast<int2 *>(p.out_i32) + kofs + (long)f0 * npp;      // kofs: integration of a batch
+    float2 *const of = p.out_f32 + kofs + (long)f0 * npp;
     const bool has_i = p.out_i32 != nullptr, has_f = p.out_f32 != nullptr;
     const bool rmw = p.accumulate != 0, redo = p.split && p.nslice <= 1;
     const float scale = p.scale;
@@ -221,9 +306,12 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
     // channel group, each integrates a slice of the time steps, and the partial visibilities meet
     // through distributed shared memory (no atomics, no workspace, no second kernel).
     const bool clustered = p.nslice > 1;
-    int s0, s1, slice = 0, grp_c = 0;
+    int s0, s1, slice = 0, grp_c = 0, kb = 0;
     if (p.nslice > 0) {
-        grp_c = clustered ? blockIdx.x / p.nslice : blockIdx.x;
+        // batched launches (p.nbatch integrations back to back in memory, one grid): CTA = (integration, group, slice)
+        const int gidx = clustered ? blockIdx.x / p.nslice : blockIdx.x;
+        kb = gidx / ngroups;
+        grp_c = gidx - kb * ngroups;
         slice = clustered ? blockIdx.x % p.nslice : 0;
         const int len = (nst + p.nslice - 1) / p.nslice;
         s0 = grp_c * nst + slice * len;
@@ -233,8 +321,17 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
         s0 = (int)(total * blockIdx.x / gridDim.x);
         s1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
     } else {
-        s0 = (int)((long)ngroups * blockIdx.x / gridDim.x) * nst;
-        s1 = (int)((long)ngroups * (blockIdx.x + 1) / gridDim.x) * nst;
+        // whole groups per CTA, persistent: CTA c takes every gridDim.x-th VIRTUAL group (integration of the batch,
+        // channel group); the pipeline below runs across group boundaries, so the write-out of one group overlaps
+        // the loads of the next.  Strided, not a contiguous share: the CTAs that run together then work on neighbouring channel groups of the
+        // same integration, i.e. on neighbouring 32 B runs of the same (t, station) rows, which is what lets the DRAM
+        // controllers serve them from open pages (a contiguous share per CTA scatters the 148 streams over as many
+        // rows: measured 43 instead of 12 us per integration).  Local stage index n -> local group n / nst ->
+        // virtual group blockIdx.x + (n / nst) * gridDim.x.
+        const int vg = ngroups * p.nbatch;
+        const int mine = vg > (int)blockIdx.x ? (vg - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        s0 = 0;
+        s1 = mine * nst;
     }
     // a time slice may be empty (more slices than stages); it still takes part in the slice fix-up
     const int nstages = max(0, s1 - s0);
@@ -275,15 +372,27 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
         // ---- TMA producer ----
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-            int grp = s0 / nst, st = s0 - grp * nst;
+            int grp = s0 / nst, st = s0 - grp * nst, kl = kb;
+            const bool strided = p.nslice <= 0 && !p.split;
+            int gv = blockIdx.x;                               // strided: virtual group -> (integration, group)
+            if (strided) {
+                kl = gv / ngroups;
+                grp = gv - kl * ngroups;
+            }
             for (int n = 0; n < nstages; n++) {
                 const int r = n % TM_NR;
                 if (n >= TM_NR) tc_mbar_wait(&rempty[r], (uint32_t)(n / TM_NR - 1) & 1u);
                 tm_expect_tx(&rfull[r], TM_RAWB);
-                tm_load_3d(raw_addr + r * TM_RAWB, &tmap, &rfull[r], (p.f_off + grp * FC) * NPOL * 2, st * KT, 0);
+                tm_load_4d(raw_addr + r * TM_RAWB, &tmap, &rfull[r], (p.f_off + grp * FC) * NPOL * 2, st * KT, 0, kl);
                 if (++st == nst) {
                     st = 0;
-                    grp++;
+                    if (strided) {
+                        gv += gridDim.x;
+                        kl = gv / ngroups;
+                        grp = gv - kl * ngroups;
+                    } else {
+                        grp++;
+                    }
                 }
             }
         }
@@ -380,9 +489,17 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
             // image ring is free: the 16 channels are combined (re/im rows sit in adjacent lanes), staged
             // there in OUTPUT order [channel][baseline][pol^2](re, im) and leave as ONE contiguous block
             // (the output is channel-major, lib/clXEngine_impl.cc:799-806).
-            const int grp_e = (p.nslice > 0) ? grp_c : sg / nst;
+            int grp_e = grp_c, kb_e = kb;
+            if (p.nslice <= 0) {
+                grp_e = sg / nst;
+                if (!p.split) {                                        // strided virtual groups
+                    const int gv = blockIdx.x + grp_e * gridDim.x;
+                    kb_e = gv / ngroups;
+                    grp_e = gv - kb_e * ngroups;
+                }
+            }
             const int f0 = grp_e * FC;
-            if (nstages > 0) {
+            if (nstages > 0 && !(p.dbg & 2)) {
                 const int wq = warp & 3;
                 const int v1 = 8 * wq + ((lane & 15) >> 1), c1 = lane & 1;
                 const int st1 = (NPOL == 1) ? v1 : (v1 >> 1);
@@ -415,10 +532,13 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
                 tc_fence_before();                                     // TMEM is drained
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(tfree);
+            } else if (nstages > 0) {
+                if (lane == 0) tc_mbar_arrive(tfree);
             }
             if (clustered) break;                                      // the exchange below needs every thread
             tm_worker_sync();
-            tm_write_out<NPOL>(p, stg, nullptr, 0, 0, spp, npp, f0, min(FC, p.F - f0), tid);
+            if (!(p.dbg & 1))
+                tm_write_out<NPOL>(p, stg, nullptr, 0, 0, spp, npp, f0, min(FC, p.F - f0), tid, (long)kb_e * p.F * npp);
             tm_worker_sync();
         }
     }
@@ -462,7 +582,28 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
         }
         tm_mbar_wait_cluster(pdata, 0);
         tm_write_out<NPOL>(p, stg + slice * blk, reinterpret_cast<const int2 *>(sptr), CL - 1, blk, spp, npp, f0,
-                           min(nc, p.F - f0), tid);
+                           min(nc, p.F - f0), tid, (long)kb * p.F * npp);
+    }
+    if (p.ngather > 0 && p.gather_counter != nullptr && warp < XE_WARPS) {
+        // ---- "my slab is complete everywhere": every CTA fences its peer stores and counts itself in; the last
+        // one releases this rank's flag on every rank (one multicast store, or one peer store per rank).  A consumer
+        // acquires the flags on the device (k_gather_wait): no host barrier between the kernel and its readers. ----
+        __threadfence_system();
+        tm_worker_sync();
+        if (threadIdx.x == 0) {
+            const unsigned old = atomicAdd(p.gather_counter, 1u);
+            if (old == gridDim.x - 1) {
+                atomicExch(p.gather_counter, 0u);                      // ready for the next launch
+                __threadfence_system();
+                if (p.gather_flag_mc != nullptr) {
+                    asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(p.gather_flag_mc), "r"(p.gather_epoch) : "memory");
+                } else {
+                    for (int g = 0; g < p.ngather; g++)
+                        if (p.gather_flag[g] != nullptr)
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.gather_flag[g]), "r"(p.gather_epoch) : "memory");
+                }
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -494,17 +635,18 @@ inline tm_encode_fn tm_encoder()
     }();
     return fn;
 }
-// dims (innermost first): row bytes | time (stride A*rowb) | station (stride rowb); box IB x 32 x ASTN
-inline bool tm_make_map(CUtensorMap *tm, const void *base, long rowb, int A, int T, int npol, int fc, int l2promo)
+// dims (innermost first): row bytes | time (stride A*rowb) | station (stride rowb) | integration of a batch (stride
+// T*A*rowb); box IB x KT x ASTN x 1.  Whatever a box covers beyond a dimension is zero-filled, per dimension.
+inline bool tm_make_map(CUtensorMap *tm, const void *base, long rowb, int A, int T, int npol, int fc, int l2promo, int nbatch)
 {
     tm_encode_fn enc = tm_encoder();
     if (!enc) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)rowb, (cuuint64_t)T, (cuuint64_t)A};
-    const cuuint64_t strides[2] = {(cuuint64_t)rowb * A, (cuuint64_t)rowb};
+    const cuuint64_t dims[4] = {(cuuint64_t)rowb, (cuuint64_t)T, (cuuint64_t)A, (cuuint64_t)nbatch};
+    const cuuint64_t strides[3] = {(cuuint64_t)rowb * A, (cuuint64_t)rowb, (cuuint64_t)rowb * A * T};
     const int ib = fc * npol * 2;
-    const cuuint32_t box[3] = {(cuuint32_t)ib, (cuuint32_t)(512 / fc), (cuuint32_t)(32 / npol)};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+    const cuuint32_t box[4] = {(cuuint32_t)ib, (cuuint32_t)(512 / fc), (cuuint32_t)(32 / npol), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
                      ib == 16 ? CU_TENSOR_MAP_SWIZZLE_NONE : ib == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                      (CUtensorMapL2promotion)l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

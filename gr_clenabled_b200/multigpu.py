@@ -54,15 +54,20 @@ def gather_visibilities(local_slab, num_channels, items_per_channel, group=None)
     return torch.cat([b[:c * per] for b, c in zip(bufs, counts)])
 
 
+FLAG_STRIDE = 32          # CLB200_XENGINE_FLAG_STRIDE (uint32 words between two ranks' flags: one 128 B line each)
+
+
 class PeerGather:
     """Fused X-engine all-gather over peer memory (one process per GPU of one box).
 
-    Every rank allocates the FULL visibility matrix c32[num_channels][items_per_channel] with
-    clb200_mem_alloc, exports its interprocess handle, opens the peers' (peer access over NVLink is
+    Every rank allocates the FULL visibility matrix c32[num_channels][items_per_channel] and a small flag array
+    with clb200_mem_alloc, exports their interprocess handles, opens the peers' (peer access over NVLink is
     enabled on open) and registers all of them with its channel-sharded clXEngine handle
-    (clb200_xengine_set_gather): the correlation kernel's epilogue then stores this rank's channel slab
-    into every rank's matrix, and no collective follows the kernel.  torch.distributed only carries the
-    64-byte handles (once) and the caller's barrier."""
+    (clb200_xengine_set_gather / set_gather_sync): the correlation kernel's epilogue then stores this rank's
+    channel slab into every rank's matrix (16 B peer stores) and, once its last CTA has stored, releases its flag on
+    every rank; xe.gather_wait(stream) makes the stream wait -- on the device -- until every rank's slab of the
+    current epoch has landed.  No collective and no host barrier follow the kernel; torch.distributed only carries
+    the 64-byte handles, once."""
 
     def __init__(self, xe, device, num_channels, items_per_channel, group=None):
         import ctypes as C
@@ -73,25 +78,31 @@ class PeerGather:
         self._lib, self.device = capi.load(), device
         self.nbytes = num_channels * items_per_channel * 8
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        self.own = C.c_void_p()
+        self.own, self.own_flags = C.c_void_p(), C.c_void_p()
         capi.check(self._lib.clb200_mem_alloc(device, self.nbytes, C.byref(self.own)))
-        h = C.create_string_buffer(64)
+        capi.check(self._lib.clb200_mem_alloc(device, world * FLAG_STRIDE * 4, C.byref(self.own_flags)))
+        h, hf = C.create_string_buffer(64), C.create_string_buffer(64)
         capi.check(self._lib.clb200_ipc_export(device, self.own, h))
+        capi.check(self._lib.clb200_ipc_export(device, self.own_flags, hf))
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(h.raw), group=group)
-        self.ptrs, self._opened = [], []
+        dist.all_gather_object(handles, (bytes(h.raw), bytes(hf.raw)), group=group)
+        self.ptrs, self.flag_ptrs, self._opened = [], [], []
         for r in range(world):
             if r == rank:
                 self.ptrs.append(self.own.value)
+                self.flag_ptrs.append(self.own_flags.value)
                 continue
-            p = C.c_void_p()
-            capi.check(self._lib.clb200_ipc_open(device, C.create_string_buffer(handles[r], 64), C.byref(p)))
+            p, pf = C.c_void_p(), C.c_void_p()
+            capi.check(self._lib.clb200_ipc_open(device, C.create_string_buffer(handles[r][0], 64), C.byref(p)))
+            capi.check(self._lib.clb200_ipc_open(device, C.create_string_buffer(handles[r][1], 64), C.byref(pf)))
             self.ptrs.append(p.value)
-            self._opened.append(p)
+            self.flag_ptrs.append(pf.value)
+            self._opened += [p, pf]
         xe.set_gather(self.ptrs)
+        xe.set_gather_sync(rank, self.flag_ptrs)
 
     def result(self):
-        """this rank's full matrix as complex64 (call after every rank's stream has drained + a barrier)"""
+        """this rank's full matrix as complex64 (after xe.gather_wait + a stream sync, or a barrier)"""
         import ctypes as C
 
         import numpy as np
@@ -102,10 +113,52 @@ class PeerGather:
         return out
 
     def close(self):
-        from . import capi
         for p in self._opened:
             self._lib.clb200_ipc_close(self.device, p)
         self._opened = []
         if self.own:
             self._lib.clb200_mem_free(self.device, self.own)
-            self.own = None
+            self._lib.clb200_mem_free(self.device, self.own_flags)
+            self.own = self.own_flags = None
+
+
+class MulticastGather:
+    """The same fused gather through an NVSwitch MULTICAST object: the matrix and the flag array live in one
+    torch symmetric-memory allocation (torch.distributed._symmetric_memory: cuMemCreate + cuMulticastBindMem on every
+    rank, the plumbing this module leaves to torch), and the kernel's epilogue issues ONE `multimem.st` per 16 B --
+    the switch replicates it into every rank's copy -- instead of one peer store per rank: 1/N of the NVLink egress.
+    Raises RuntimeError when the box has no multicast support (then use PeerGather)."""
+
+    def __init__(self, xe, device, num_channels, items_per_channel, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nbytes = num_channels * items_per_channel * 8
+        mat_words = (self.nbytes + 255) // 256 * 64                       # matrix, padded to 256 B
+        self.t = symm_mem.empty(mat_words + world * FLAG_STRIDE, dtype=torch.float32, device=torch.device("cuda", device))
+        self.t.zero_()
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:                                                  # noqa: BLE001 -- not needed on newer torch
+            pass
+        self.hdl = symm_mem.rendezvous(self.t, group.group_name)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("no multicast address for the symmetric allocation (NVLS unavailable)")
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        xe.set_gather(ptrs)
+        xe.set_gather_sync(rank, [p + mat_words * 4 for p in ptrs], mc, mc + mat_words * 4)
+        self.mat_words = mat_words
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+    def result(self):
+        import numpy as np
+        return self.t[:self.nbytes // 4].cpu().numpy().view(np.complex64)
+
+    def close(self):
+        self.hdl = None
+        self.t = None

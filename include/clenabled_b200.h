@@ -242,6 +242,12 @@ CLB200_API int clb200_xengine_poll_result(clb200_handle h, void *out_c32, int wa
 CLB200_API int clb200_xengine_stream_state(clb200_handle h, long *tracker, long *integrations, long *results_pending,
                                            uint64_t *pushes, uint64_t *pushes_blocked);
 CLB200_API int clb200_xengine_stream_end(clb200_handle h);
+/* nbatch integrations that lie back to back in device memory (IChar), matrices back to back in d_out_c32: ONE grid
+ * of nbatch x (channel groups x time slices) CTAs, so the per-launch fixed cost (first-load latency, exchange,
+ * write-out, drain) of one integration overlaps the streaming phase of the others and all SMs stay busy
+ * (128 CTAs per 32 x 1024 x 1024 integration leave 20 of 148 SMs idle when launched one by one).       */
+CLB200_API int clb200_xengine_launch_device_batch(clb200_handle h, const void *d_in, void *d_out_c32, int nbatch,
+                                                  void *stream);
 /* channel-sharded variant for multi-GPU: this handle owns channels
  * [chan_first, chan_first+chan_count) of an integration whose host layout has
  * total_channels per station; work() gathers only that slab (cudaMemcpy2D).      */
@@ -250,12 +256,25 @@ CLB200_API int clb200_xengine_set_shard(clb200_handle h, int total_channels, int
  * full visibility matrix of EVERY rank (its own + the peers', opened with clb200_ipc_open); the
  * correlation kernel's epilogue then writes this rank's channel slab straight into all of them
  * (c32[total_channels][baselines][pol^2] at channel offset chan_first), so no collective follows the
- * kernel.  The matrices are complete once every rank's stream has drained (a barrier of the caller's).
+ * kernel.  The matrices are complete once every rank's stream has drained (a barrier of the caller's), or -- without
+ * any host barrier -- once clb200_xengine_gather_wait has run (set_gather_sync below).
  * Needs clb200_xengine_set_shard first and 16 B aligned input rows (the TMA kernel).               */
 #define CLB200_XENGINE_MAX_GATHER 8
 CLB200_API int clb200_xengine_set_gather(clb200_handle h, int nranks, void *const *full_out_c32);
 /* d_in: this rank's channel slab only, [t][station][shard channels][pol]                            */
 CLB200_API int clb200_xengine_launch_device_gather(clb200_handle h, const void *d_in, void *stream);
+/* Device-side completion of the fused gather (replaces the caller's barrier) and NVSwitch multicast:
+ * flag_arrays[r] = rank r's flag array (uint32[nranks * CLB200_XENGINE_FLAG_STRIDE], zero-initialised, peer-mapped
+ * like the matrices).  After its last CTA has stored, a launch release-stores its epoch (1, 2, ... per launch) into
+ * word [my_rank * STRIDE] of EVERY rank's array; clb200_xengine_gather_wait enqueues a one-warp kernel that acquires
+ * all nranks words of the local array, so whatever follows it on that stream reads a complete matrix.
+ * multicast_out / multicast_flags (optional, both or neither): multicast addresses of the matrix and of the flag
+ * array bound on every rank (cuMulticast* / torch symmetric memory); the slab and the flag then leave as ONE
+ * `multimem.st` each and the switch replicates them, instead of one peer store per rank.               */
+#define CLB200_XENGINE_FLAG_STRIDE 32
+CLB200_API int clb200_xengine_set_gather_sync(clb200_handle h, int my_rank, void *const *flag_arrays,
+                                              void *multicast_out, void *multicast_flags);
+CLB200_API int clb200_xengine_gather_wait(clb200_handle h, void *stream);
 
 /* ------------------------------------------------- device memory for peers -- */
 /* cudaMalloc'ed buffers whose interprocess handle (64 opaque bytes) other ranks of the same box can

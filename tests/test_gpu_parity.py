@@ -411,6 +411,33 @@ def test_xengine_channel_shard_matches_full():
     assert np.array_equal(np.concatenate(parts, axis=0), full)
 
 
+@pytest.mark.parametrize("A,F,T,npol,K", [(32, 64, 256, 1, 5), (32, 1024, 64, 1, 3), (16, 40, 100, 2, 4), (8, 2400, 32, 1, 2),
+                                           (5, 7, 33, 1, 3)])
+def test_xengine_batched_launch_equals_single_launches(A, F, T, npol, K):
+    """clb200_xengine_launch_device_batch: K integrations back to back, one grid (4-D tensor map, the batch index is the
+    outermost coordinate, so ragged T / stations / channels are zero-filled per integration); rows that are not 16 B
+    aligned fall back to K launches -- either way every matrix equals the single launch and the oracle"""
+    import torch
+    per = T * A * F * npol * 2
+    buf = orc.rng_i8(per * K, orc.SEED_X + 60)
+    d_in = torch.from_numpy(buf).cuda()
+    nout = F * (A * (A + 1) // 2) * npol * npol
+    d_out = torch.zeros(K * nout * 2, dtype=torch.float32, device="cuda")
+    d_one = torch.zeros(nout * 2, dtype=torch.float32, device="cuda")
+    blk = _xe(capi.DTYPE_BYTE, npol, A, F, T)
+    sp = torch.cuda.current_stream().cuda_stream
+    blk.launch_device_batch(d_in.data_ptr(), d_out.data_ptr(), K, sp)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.complex64).reshape(K, nout)
+    for k in range(K):
+        blk.launch_device(d_in.data_ptr() + k * per, d_one.data_ptr(), False, sp)
+        torch.cuda.synchronize()
+        assert np.array_equal(got[k], d_one.cpu().numpy().view(np.complex64)), k
+    want = orc.xengine_exact(buf[(K - 1) * per:], A, F, T, npol).astype(np.float64) / (127.0 * 127.0)
+    assert np.max(np.abs(got[K - 1].real - want[:, 0])) < 1e-3 * max(1.0, np.max(np.abs(want)))
+    assert np.max(np.abs(got[K - 1].imag - want[:, 1])) < 1e-3 * max(1.0, np.max(np.abs(want)))
+
+
 def _ports_of(buf, T, A, F, npol, sb, planar):
     """the block's input streams for an integration buffer [t][station][chan][pol](sample): one array per station
     (per station and polarisation for unpacked two-polarisation data), each [t][chan]"""
@@ -559,6 +586,12 @@ def test_xengine_fused_gather_writes_every_registered_matrix():
         p = C.c_void_p()
         capi.check(lib.clb200_mem_alloc(0, F * nbl * 8, C.byref(p)))
         mats.append(p)
+    # completion flags: one array per 'rank'; a launch releases its epoch into every array, gather_wait acquires them
+    flags = []
+    for _ in range(2):
+        p = C.c_void_p()
+        capi.check(lib.clb200_mem_alloc(0, 2 * 32 * 4, C.byref(p)))
+        flags.append(p)
     b4 = buf.reshape(T, A, F, 2)
     sp = torch.cuda.current_stream().cuda_stream
     keep = []
@@ -566,10 +599,25 @@ def test_xengine_fused_gather_writes_every_registered_matrix():
         blk = _xe(capi.DTYPE_BYTE, 1, A, F // 2, T)
         blk.set_shard(F, r * (F // 2))
         blk.set_gather([m.value for m in mats])
+        blk.set_gather_sync(r, [f.value for f in flags])
         slab = torch.from_numpy(np.ascontiguousarray(b4[:, :, r * (F // 2):(r + 1) * (F // 2), :])).cuda()
-        blk.launch_device_gather(slab.data_ptr(), sp)
         keep.append((blk, slab))
+    side = torch.cuda.Stream()
+    for epoch in (1, 2, 3):                                   # rank 1 launches on another stream; rank 0's stream waits on the flags
+        with torch.cuda.stream(side):
+            keep[1][0].launch_device_gather(keep[1][1].data_ptr(), side.cuda_stream)
+        keep[0][0].launch_device_gather(keep[0][1].data_ptr(), sp)
+        keep[0][0].gather_wait(sp)
+        torch.cuda.current_stream().synchronize()             # only rank 0's stream: the flags guarantee rank 1's slab
+        fl = np.zeros(2 * 32, np.uint32)
+        capi.check(lib.clb200_mem_copy_to_host(0, flags[0], fl.ctypes.data_as(C.c_void_p), fl.nbytes))
+        assert fl[0] == epoch and fl[32] == epoch
+        got = np.zeros(F * nbl, np.complex64)
+        capi.check(lib.clb200_mem_copy_to_host(0, mats[0], got.ctypes.data_as(C.c_void_p), got.nbytes))
+        assert np.max(np.abs(got.real - want[:, 0])) < 1e-3 and np.max(np.abs(got.imag - want[:, 1])) < 1e-3
     torch.cuda.synchronize()
+    for f in flags:
+        capi.check(lib.clb200_mem_free(0, f))
     for m in mats:
         got = np.zeros(F * nbl, np.complex64)
         capi.check(lib.clb200_mem_copy_to_host(0, m, got.ctypes.data_as(C.c_void_p), got.nbytes))
