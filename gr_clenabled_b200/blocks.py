@@ -382,6 +382,9 @@ class clXEngine(_Block):
         return {"tracker": t.value, "integrations": n.value, "results_pending": r.value,
                 "pushes": p.value, "pushes_blocked": b.value}
 
+    def stream_ports_stable(self, stable=True):
+        check(self._lib.clb200_xengine_stream_ports_stable(self._h, int(stable)))
+
     def stream_end(self):
         check(self._lib.clb200_xengine_stream_end(self._h))
 

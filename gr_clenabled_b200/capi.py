@@ -83,6 +83,7 @@ SIGNATURES = {
     "clb200_pfb_create": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _i, _ph]),
     "clb200_pfb_work": (_i, [_vp, _vp, _vp, _l]),
     "clb200_pfb_launch_device": (_i, [_vp, _vp, _vp, _l, _vp]),
+    "clb200_probe_fp32": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "clb200_describe": (_i, [_vp, C.c_char_p, _i]),
     "clb200_set_debug": (_i, [_vp, _i]),
     "clb200_xengine_create": (_i, [_i, _i, _i, _i, _i, _i, _ph]),
@@ -97,6 +98,7 @@ SIGNATURES = {
     "clb200_xengine_push_timesteps": (_i, [_vp, _ph, _i, _l]),
     "clb200_xengine_poll_result": (_i, [_vp, _vp, _i, _pi]),
     "clb200_xengine_stream_state": (_i, [_vp, _pl, _pl, _pl, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "clb200_xengine_stream_ports_stable": (_i, [_vp, _i]),
     "clb200_xengine_stream_end": (_i, [_vp]),
     "clb200_xengine_set_shard": (_i, [_vp, _i, _i]),
     "clb200_xengine_set_gather": (_i, [_vp, _i, _ph]),

@@ -74,6 +74,14 @@ struct XeParams {
     unsigned gather_epoch;
 };
 
+struct XeGatherSync {
+    unsigned *flag[8];          // rank r's flag word for this source rank
+    unsigned *flag_mc;          // multicast address of the same word (or null)
+    const unsigned *local;      // this rank's flag array
+    unsigned epoch;
+    int nranks, signal, wait;
+};
+
 // which row tiles warp share Q of WPC owns
 template <int WPC, int Q>
 __host__ __device__ constexpr bool owns(int mi)
@@ -422,16 +430,59 @@ __global__ void k_xengine_c32(const float2 *__restrict__ in, float2 *__restrict_
     }
 }
 
-// consumer side of the fused gather: lane r acquires rank r's flag until it carries `epoch` (or a later one)
-__global__ void k_gather_wait(const unsigned *flags, int nranks, unsigned epoch)
+// Streaming ingest from page-locked ports: the SMs read the ports over PCIe themselves (zero-copy loads, 16 B per lane,
+// thousands in flight) and write the [t][station][chan] integration buffer -- one launch per push instead of one
+// 2-D DMA per station (cudaMemcpy2DAsync of 1-2 KiB rows reaches ~27 GB/s of the link's 55).
+struct XeIngest {
+    const char *port[64];
+    char *dst;                  // first time step of this push in the device integration buffer
+    long ntime;
+    int nports, row16;          // 16 B units per (t, station) row of this handle's slab
+    long src_pitch, src_off;    // bytes between two time steps of a port / offset of the slab inside a port item
+    long frame;                 // bytes per time step in the device buffer
+};
+__global__ void __launch_bounds__(256) k_xe_ingest(XeIngest g)
 {
+    const long per_t = (long)g.nports * g.row16;              // 16 B units per time step
+    const long total = per_t * g.ntime;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long t = i / per_t;
+        const int r = (int)(i - t * per_t);
+        const int s = r / g.row16, c = r - s * g.row16;
+        const int4 v = __ldcs(reinterpret_cast<const int4 *>(g.port[s] + t * g.src_pitch + g.src_off) + c);
+        reinterpret_cast<int4 *>(g.dst + t * g.frame + (long)s * g.row16 * 16)[c] = v;
+    }
+}
+
+// completion of the fused gather, stream-ordered behind the correlation kernel (whose peer stores have all been
+// performed when it completes): lane r releases THIS rank's flag on rank r -- or lane 0 on every rank at once through
+// the multicast address -- then acquires rank r's flag in the local array until it carries `epoch` (or a later one).
+// What follows on the stream reads a complete matrix; no host barrier, no fence inside the hot kernel.
+__global__ void k_gather_signal_wait(XeGatherSync g)
+{
+    // launched with programmatic stream serialisation: it is resident before the correlation kernel ends (its launch
+    // latency is off the critical path) and lets the NEXT correlation kernel run its prologue meanwhile
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");            // the correlation kernel and its peer stores are complete
     const int r = threadIdx.x;
-    if (r < nranks) {
-        const unsigned *f = flags + (size_t)r * CLB200_XENGINE_FLAG_STRIDE;
+    if (g.signal) {
+        if (g.flag_mc != nullptr) {
+            if (r == 0) asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(g.flag_mc), "r"(g.epoch) : "memory");
+        } else if (r < g.nranks && g.flag[r] != nullptr) {
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.flag[r]), "r"(g.epoch) : "memory");
+        }
+    }
+    if (g.wait && r < g.nranks) {
+        const unsigned *f = g.local + (size_t)r * CLB200_XENGINE_FLAG_STRIDE;
         unsigned v;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        } while ((int)(v - epoch) < 0);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) __trap();       // a rank that never signals: fail (CUDA error) instead of hanging
+        } while ((int)(v - g.epoch) < 0);
     }
 }
 
@@ -506,6 +557,8 @@ struct XEngine : clb200_block {
         cudaEvent_t ev_h2d[2] = {}, ev_kern[2] = {};          // uploads of buffer b landed / kernel on buffer b done
         cudaEvent_t ev_kres[MAXRES] = {}, ev_res[MAXRES] = {}; // matrix r computed / copied to the host
         bool pin_dirty[2] = {false, false};    // pinned staging b still has uploads in flight
+        bool dma_ingest = false;               // CLB200_XE_INGEST_DMA=1: one 2-D DMA per station instead of the ingest kernel
+        bool ports_stable = false;             // page-locked ports stay untouched until their integration's result is polled
         long tracker = 0;                      // time steps of the current integration ingested so far
         long n_integ = 0;                      // integrations handed to the GPU
         long res_head = 0, res_tail = 0;       // results launched / delivered
@@ -682,11 +735,17 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     for (int r = 0; r < 8; r++) p.gather_flag[r] = nullptr;
     if (gather && x->gather_rank >= 0) {
         p.gather_mc = (float2 *)x->gather_mc;
-        p.gather_counter = (unsigned *)x->d_gather_counter.p;
         p.gather_epoch = ++x->gather_epoch;
-        if (x->gather_flags_mc) p.gather_flag_mc = x->gather_flags_mc + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE;
-        for (int r = 0; r < x->ngather; r++)
-            p.gather_flag[r] = x->gather_flags[r] ? x->gather_flags[r] + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE : nullptr;
+        // CLB200_XE_GATHER_INKERNEL=1: the kernel's last CTA releases the flags itself (every CTA then waits for the
+        // acknowledgement of its peer stores before it leaves its SM: measured 27.8 vs ... us per launch at 2 GPUs);
+        // default: the flags are released by the one-warp kernel that clb200_xengine_gather_wait enqueues behind it
+        static const bool inkernel = [] { const char *e = getenv("CLB200_XE_GATHER_INKERNEL"); return e && atoi(e); }();
+        if (inkernel) {
+            p.gather_counter = (unsigned *)x->d_gather_counter.p;
+            if (x->gather_flags_mc) p.gather_flag_mc = x->gather_flags_mc + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE;
+            for (int r = 0; r < x->ngather; r++)
+                p.gather_flag[r] = x->gather_flags[r] ? x->gather_flags[r] + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE : nullptr;
+        }
     }
     if (gather) {
         CLB_CHECK(tma, CLB200_ESTATE, "clXEngine: the peer-memory gather needs the TMA kernel (16 B aligned rows, <= 32 inputs x pols)");
@@ -833,6 +892,10 @@ int xe_stream_begin(XEngine *x, int pipeline, int nres)
     CLB_TRY(xe_init_streams(x));
     st.pipeline = pipeline > 1 ? pipeline : 1;
     st.nres = nres;
+    {
+        const char *e = getenv("CLB200_XE_INGEST_DMA");
+        st.dma_ingest = e && atoi(e);
+    }
     const size_t in_bytes = (size_t)x->T * x->A * x->F * x->npol * x->sample_bytes();      // this handle's slab
     const size_t out_bytes = (size_t)x->out_items() * 8;
     CLB_CUDA(cudaStreamCreateWithFlags(&st.s_h2d, cudaStreamNonBlocking));
@@ -924,9 +987,28 @@ int xe_stream_push(XEngine *x, const void *const *ports, int nports, long ntime)
         }
         char *dst_dev = (char *)st.dev[b].p + (size_t)st.tracker * frame;
         if (direct) {
-            for (int s = 0; s < x->A; s++)
-                CLB_CUDA(cudaMemcpy2DAsync(dst_dev + s * row, frame, (const char *)ports[s] + (size_t)done * vec_in + off_in,
-                                           vec_in, row, (size_t)n, cudaMemcpyHostToDevice, st.s_h2d));
+            bool by_kernel = x->A <= 64 && row % 16 == 0 && vec_in % 16 == 0 && off_in % 16 == 0 && !st.dma_ingest;
+            for (int s = 0; by_kernel && s < x->A; s++) by_kernel = ((uintptr_t)ports[s] % 16) == 0;
+            if (by_kernel) {
+                XeIngest g;
+                for (int s = 0; s < x->A; s++) g.port[s] = (const char *)ports[s] + (size_t)done * vec_in;
+                g.dst = dst_dev;
+                g.ntime = n;
+                g.nports = x->A;
+                g.row16 = (int)(row / 16);
+                g.src_pitch = (long)vec_in;
+                g.src_off = (long)off_in;
+                g.frame = (long)frame;
+                const long units = (long)n * x->A * g.row16;
+                const int grid = grid_for((units + 1023) / 1024, device_sm_count(x->device), 4);
+                k_xe_ingest<<<grid, 256, 0, st.s_h2d>>>(g);
+                CLB_CUDA(cudaGetLastError());
+                x->n_launch++;
+            } else {
+                for (int s = 0; s < x->A; s++)
+                    CLB_CUDA(cudaMemcpy2DAsync(dst_dev + s * row, frame, (const char *)ports[s] + (size_t)done * vec_in + off_in,
+                                               vec_in, row, (size_t)n, cudaMemcpyHostToDevice, st.s_h2d));
+            }
         } else {
             char *stage = (char *)st.pin[b].p + (size_t)st.tracker * frame;
             for (long t = 0; t < n; t++) {
@@ -958,7 +1040,9 @@ int xe_stream_push(XEngine *x, const void *const *ports, int nports, long ntime)
         x->n_h2d += (size_t)n * frame;
         st.tracker += n;
         done += n;
-        if (direct) CLB_CUDA(cudaStreamSynchronize(st.s_h2d));        // the ports are the caller's again on return
+        // the ports are the caller's again on return -- unless the caller has promised to leave them alone
+        // (clb200_xengine_stream_ports_stable): then the DMA of this push overlaps the caller's next one
+        if (direct && !st.ports_stable) CLB_CUDA(cudaStreamSynchronize(st.s_h2d));
         if (st.tracker == x->T) {
             CLB_TRY(xe_stream_launch(x, b));
             st.tracker = 0;
@@ -1139,8 +1223,25 @@ int clb200_xengine_gather_wait(clb200_handle h, void *stream)
     CLB_TRY(check_kind(h, KIND_XENGINE, &x));
     CLB_CHECK(x->gather_rank >= 0, CLB200_ESTATE, "clXEngine: set_gather_sync first");
     DeviceGuard g(x->device);
-    k_gather_wait<<<1, 32, 0, (cudaStream_t)stream>>>(x->gather_flags[x->gather_rank], x->ngather, x->gather_epoch);
-    CLB_CUDA(cudaGetLastError());
+    XeGatherSync gs;
+    for (int r = 0; r < 8; r++)
+        gs.flag[r] = (r < x->ngather && x->gather_flags[r]) ? x->gather_flags[r] + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE : nullptr;
+    gs.flag_mc = x->gather_flags_mc ? x->gather_flags_mc + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE : nullptr;
+    gs.local = x->gather_flags[x->gather_rank];
+    gs.epoch = x->gather_epoch;
+    gs.nranks = x->ngather;
+    gs.signal = 1;
+    gs.wait = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = x->pdl ? 1 : 0;
+    CLB_CUDA(cudaLaunchKernelEx(&cfg, k_gather_signal_wait, gs));
     x->n_launch++;
     return CLB200_OK;
 }
@@ -1260,6 +1361,16 @@ int clb200_xengine_stream_state(clb200_handle h, long *tracker, long *integratio
     if (results_pending) *results_pending = x->st.res_head - x->st.res_tail;
     if (pushes) *pushes = x->st.n_push;
     if (pushes_blocked) *pushes_blocked = x->st.n_blocked;
+    return CLB200_OK;
+}
+
+int clb200_xengine_stream_ports_stable(clb200_handle h, int stable)
+{
+    XEngine *x;
+    CLB_TRY(check_kind(h, KIND_XENGINE, &x));
+    std::lock_guard<std::mutex> lk(x->mtx);
+    CLB_CHECK(x->st.on, CLB200_ESTATE, "clXEngine: stream_begin first");
+    x->st.ports_stable = stable != 0;
     return CLB200_OK;
 }
 

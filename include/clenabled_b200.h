@@ -96,6 +96,11 @@ CLB200_API int clb200_get_counters(clb200_handle h, uint64_t *h2d, uint64_t *d2h
 CLB200_API int clb200_describe(clb200_handle h, char *buf, int buflen);
 CLB200_API int clb200_set_debug(clb200_handle h, int on);
 
+/* Measured FP32 pipe peaks of the device (a ~10 ms probe): FFMA in TFLOP/s (2 flop per lane and clock), plain and
+ * packed (add.f32x2) additions in TFLOP/s (1 flop per lane and clock).  The compute-side roofline denominators of the
+ * FP32-bound kernels (FFT filter, time-domain FIR) in bench.py.                                         */
+CLB200_API int clb200_probe_fp32(int device, double *ffma_tflops, double *fadd_tflops, double *fadd2_tflops);
+
 /* Optional: page-lock a caller-owned host range (e.g. a GNU Radio circular buffer,
  * once, in start()) so that work() calls on it skip the staging copy and are DMA'd /
  * read by the kernels in place.  The range must stay valid until unregistered.   */
@@ -241,6 +246,10 @@ CLB200_API int clb200_xengine_push_timesteps(clb200_handle h, const void *const 
 CLB200_API int clb200_xengine_poll_result(clb200_handle h, void *out_c32, int wait, int *ready);
 CLB200_API int clb200_xengine_stream_state(clb200_handle h, long *tracker, long *integrations, long *results_pending,
                                            uint64_t *pushes, uint64_t *pushes_blocked);
+/* page-locked ports only: the caller promises that the memory handed to push_timesteps stays valid and unchanged until
+ * the result of the integration it belongs to has been polled (a capture ring it owns, not a scheduler buffer).  push
+ * then returns without waiting for the DMA to have read the ports, so uploads overlap the caller's next push.    */
+CLB200_API int clb200_xengine_stream_ports_stable(clb200_handle h, int stable);
 CLB200_API int clb200_xengine_stream_end(clb200_handle h);
 /* nbatch integrations that lie back to back in device memory (IChar), matrices back to back in d_out_c32: ONE grid
  * of nbatch x (channel groups x time slices) CTAs, so the per-launch fixed cost (first-load latency, exchange,
@@ -266,8 +275,11 @@ CLB200_API int clb200_xengine_launch_device_gather(clb200_handle h, const void *
 /* Device-side completion of the fused gather (replaces the caller's barrier) and NVSwitch multicast:
  * flag_arrays[r] = rank r's flag array (uint32[nranks * CLB200_XENGINE_FLAG_STRIDE], zero-initialised, peer-mapped
  * like the matrices).  After its last CTA has stored, a launch release-stores its epoch (1, 2, ... per launch) into
- * word [my_rank * STRIDE] of EVERY rank's array; clb200_xengine_gather_wait enqueues a one-warp kernel that acquires
- * all nranks words of the local array, so whatever follows it on that stream reads a complete matrix.
+ * word [my_rank * STRIDE] of EVERY rank's array -- by default from the one-warp kernel that clb200_xengine_gather_wait
+ * enqueues behind the launch (so the hot kernel carries no system-scope fence), which then acquires all nranks words
+ * of the local array: whatever follows it on that stream reads a complete matrix.  EVERY rank calls gather_wait after
+ * each gather launch (it is also what announces the rank's own slab); a rank that never does makes the others' wait
+ * kernels fail after 10 s instead of hanging.
  * multicast_out / multicast_flags (optional, both or neither): multicast addresses of the matrix and of the flag
  * array bound on every rank (cuMulticast* / torch symmetric memory); the slab and the flag then leave as ONE
  * `multimem.st` each and the switch replicates them, instead of one peer store per rank.               */

@@ -606,6 +606,7 @@ def test_xengine_fused_gather_writes_every_registered_matrix():
     for epoch in (1, 2, 3):                                   # rank 1 launches on another stream; rank 0's stream waits on the flags
         with torch.cuda.stream(side):
             keep[1][0].launch_device_gather(keep[1][1].data_ptr(), side.cuda_stream)
+            keep[1][0].gather_wait(side.cuda_stream)          # every rank signals (and waits) behind its launch
         keep[0][0].launch_device_gather(keep[0][1].data_ptr(), sp)
         keep[0][0].gather_wait(sp)
         torch.cuda.current_stream().synchronize()             # only rank 0's stream: the flags guarantee rank 1's slab

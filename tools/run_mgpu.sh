@@ -1,4 +1,11 @@
+# usage: bash tools/run_mgpu.sh N [probe]  -- multi-GPU checks of the round (gather arms, host-link probe)
+N=${1:-2}
 mkdir -p gpurun_out
-gr_clenabled_b200/lib/test_blocks | tail -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"; cat gpurun_out/bench_n2.json | cut -c1-1500; tail -5 gpurun_out/bench_n2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err; echo "ref n2 rc=$?"; cat gpurun_out/bench_ref_n2.json | cut -c1-600
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
+timeout 300 $TR --master-port 29511 tools/xe_gather_test.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM\|FutureWarning\|enable_symm" | tail -8 | tee gpurun_out/xe_gather_n$N.txt
+echo "== no PDL on the signal kernel"
+CLB200_XE_PDL=0 timeout 300 $TR --master-port 29514 tools/xe_gather_test.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM\|FutureWarning\|enable_symm" | tail -8 | tee gpurun_out/xe_gather_inkernel_n$N.txt
+if [ "$2" = "probe" ]; then
+timeout 200 $TR --master-port 29512 tools/h2d_probe.py 2>&1 | tail -1 | tee gpurun_out/h2d_probe_n$N.json
+fi
