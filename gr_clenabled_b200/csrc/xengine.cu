@@ -651,13 +651,41 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     // TMA kernel: 8 channels per CTA while 16 would leave SMs without a channel group (then no CTA
     // has to share a group with another one: no time slicing, no cross-CTA reduction)
     int fc = tc ? TC_FC : v->fc;
+    int want_slices = -1;                                // -1: derive from the group count below
     if (tma_ok) {
-        fc = ((x->F + 15) / 16 * 8 < sms) ? 8 : 16;      // 16 unless even 8 time slices per group leave SMs idle
+        // (channels per CTA, time slices per group) = the pair that puts the most CTAs on the SMs in ONE wave with
+        // clusters of at most 4 (measured, tools/xe_small.py: 8-CTA clusters cost 24.9 vs 12.2 us at 128 channels,
+        // 46 vs 17 us at 512).  Ties: 16 channels (32 B runs stream at 5.9 instead of 3.7 TB/s) when a CTA streams
+        // >= 384 KiB, else 8 channels with half the slices (F = 512: 15.9 vs 17.1 us).
+        long best = -1;
+        fc = 16;
+        const long in_bytes = (long)T * x->A * x->F * x->npol * 2;
+        for (int cand = 16; cand >= 8; cand -= 8) {
+            const int ng = (x->F + cand - 1) / cand, nstc = (T + 512 / cand - 1) / (512 / cand);
+            for (int sl = 1; sl <= 4; sl *= 2) {
+                if (sl > nstc || (long)ng * sl > sms) continue;
+                const long ctas = (long)ng * sl;
+                bool take = ctas > best;
+                if (ctas == best && cand == 8) take = in_bytes / ctas < 384 * 1024;
+                if (take) {
+                    best = ctas;
+                    fc = cand;
+                    want_slices = sl;
+                }
+            }
+        }
+        if (best < 0) want_slices = -1;                  // more groups than SMs either way: whole groups per CTA, 16 channels
         // two polarisations: 8 channels are already 32 B runs, and enough 8-channel groups to fill the SMs need
         // no time slicing, i.e. no exchange at all (measured 18.2 vs 20.7 us at 16 stations x 2 pols x 1024 channels)
-        if (x->npol == 2 && (x->F + 7) / 8 >= sms / 2 && (x->F + 7) / 8 <= sms) fc = 8;
+        if (x->npol == 2 && (x->F + 7) / 8 >= sms / 2 && (x->F + 7) / 8 <= sms) {
+            fc = 8;
+            want_slices = 1;
+        }
         if (nbatch > 1) fc = 16;                         // persistent over (integration, group): the widest rows
-        if (x->fc_override == 8 || x->fc_override == 16) fc = x->fc_override;
+        if (x->fc_override == 8 || x->fc_override == 16) {
+            fc = x->fc_override;
+            want_slices = -1;
+        }
     }
     const int kt = tma_ok ? 512 / fc : XE_TT;           // time steps per stage
     const int ngroups = (x->F + fc - 1) / fc;
@@ -666,6 +694,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     // few channel groups: one wave of (slice, group) CTAs; many: whole groups per CTA
     int tslices = 0;
     if (ngroups < sms && nst > 1) tslices = std::min(nst, std::max(1, sms / ngroups));
+    if (want_slices > 0) tslices = want_slices;
     {
         const char *e = getenv("CLB200_XE_SLICES");       // tuning override: 0 = stream-K split
         if (e && ngroups < 2 * sms && nst > 1) tslices = std::min(nst, atoi(e));
@@ -677,9 +706,10 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     if (nbatch > 1 && tma_ok && !batch_sliced) tslices = 0;
     else if (nbatch > 1 && tslices == 0) tslices = 1;
     if (tma_ok && tslices > 1) {
-        // the slices of a group are the CTAs of one cluster: 2, 4 or 8, each finalising fc/slices channels
+        // the slices of a group are the CTAs of one cluster: 2 or 4 (8 only on request), each finalising fc/slices channels
+        const int cap = getenv("CLB200_XE_SLICES") ? 8 : 4;
         int c = 2;
-        while (c * 2 <= std::min(tslices, std::min(8, fc))) c *= 2;
+        while (c * 2 <= std::min(tslices, std::min(cap, fc))) c *= 2;
         tslices = c;
     }
     const bool split = (tslices > 1) || (tslices == 0 && nbatch == 1 && ngroups < 2 * sms && nst > 1);
