@@ -396,37 +396,192 @@ __global__ void k_unpack4(const uint8_t *__restrict__ in, int8_t *__restrict__ o
     }
 }
 
-// complex-float input: one thread per (channel, baseline, pol pair); the float
-// accumulation runs in t order like the reference work-item (:739-810)
-__global__ void k_xengine_c32(const float2 *__restrict__ in, float2 *__restrict__ out, int A,
-                              int npol, int F, int Fstride, int f_off, int T, int accumulate)
+// ---- complex-float input (the reference's default DTYPE_COMPLEX) ---------------------------------------------
+// Per channel V = X X^H with X[(station, pol)][t] complex float: a CTA stages a tile of C32_TT time steps x NV
+// rows x C32_CH channels in shared memory (transposed so that a thread's 4 rows / 4 columns are one 32 B read each)
+// and every thread owns one 4 x 4 block of the LOWER triangle of one channel's matrix in registers: 64 FFMA per
+// 8 shared-memory loads and time step.  The sum over t runs in order inside a thread, like the reference
+// work-item's loop (lib/clXEngine_impl.cc:739-810, cxmac :729-736).  Few channel groups: the integration is also
+// split into time slices whose partial matrices are summed by a second kernel in a fixed order (deterministic).
+constexpr int C32_TT = 8;       // time steps per tile
+
+struct XeC32 {
+    const float2 *in;           // [t][station][Fstride][npol]
+    float2 *out;                // [F][nbl][npol^2] (ts == 1) or partial matrices [ts][F*nbl*npol^2]
+    int A, npol, NV, NB, nblk;  // NV = A*npol rows, NB = ceil(NV/4) blocks per side, nblk = NB(NB+1)/2
+    int F, Fstride, f_off, T, ts, accumulate;
+    int ch;                     // channels per CTA: ch * nblk <= 256 threads
+    long nout;
+};
+
+constexpr int C32_SLOTS = 4;    // 16 B staging loads per thread and tile (vector path)
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_xengine_c32_tiled(XeC32 p)
 {
-    const int nbl = A * (A + 1) / 2;
-    const long total = (long)F * nbl * npol * npol;
+    extern __shared__ __align__(16) float2 c32_smem[];          // 2 x [C32_TT][ch][NVP]
+    const int NVP = p.NB * 4;                                   // rows padded to whole blocks
+    const int CH = p.ch;
+    const int tid = threadIdx.x;
+    const int grp = blockIdx.x, slice = blockIdx.y;
+    const int f0 = grp * CH;
+    const int c = tid / p.nblk, b = tid - c * p.nblk;           // channel of the group, block of the triangle
+    const bool worker = c < CH;
+    int bi = 0, bj = 0;
+    if (worker) {
+        bi = (int)((sqrtf(8.0f * b + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= b) bi++;
+        while (bi * (bi + 1) / 2 > b) bi--;
+        bj = b - bi * (bi + 1) / 2;
+    }
+    const int tlen = (p.T + p.ts - 1) / p.ts;
+    const int t0 = slice * tlen, t1 = min(p.T, t0 + tlen);
+    float2 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+
+    const long frame = (long)p.A * p.Fstride * p.npol;          // float2 per time step
+    const int per_t = p.NV * CH;                                // values per time step of the tile
+    const int tile = C32_TT * CH * NVP;                         // float2 per staging buffer
+    // padded rows read as zero in both buffers, once
+    for (int e = tid; e < 2 * tile; e += blockDim.x) c32_smem[e] = make_float2(0.f, 0.f);
+
+    // ---- vector staging: a thread's 16 B slots are the same (t, station, pair) in every tile ----
+    // a (t, station) run holds CH * npol consecutive values = q2 float4; one float4 = two channels of one
+    // polarisation (npol 1) or the X, Y values of one channel (npol 2)
+    const int q2 = CH * p.npol / 2;
+    int sl_t[C32_SLOTS], sl_s0[C32_SLOTS], sl_s1[C32_SLOTS];
+    long sl_g[C32_SLOTS];
+    bool sl_ok0[C32_SLOTS], sl_ok1[C32_SLOTS];
+    if (VEC) {
+#pragma unroll
+        for (int k = 0; k < C32_SLOTS; k++) {
+            const int e = tid + k * blockDim.x;
+            const int t = e / (p.A * q2), r = e - t * (p.A * q2);
+            const int s = r / q2, w = r - s * q2;
+            const int ch0 = (p.npol == 1) ? 2 * w : w, ch1 = (p.npol == 1) ? 2 * w + 1 : w;
+            const int v0 = (p.npol == 1) ? s : 2 * s, v1 = (p.npol == 1) ? s : 2 * s + 1;
+            sl_t[k] = t;
+            sl_g[k] = (long)t * frame + ((long)s * p.Fstride + p.f_off + f0) * p.npol + 2 * w;
+            sl_s0[k] = (t * CH + ch0) * NVP + v0;
+            sl_s1[k] = (t * CH + ch1) * NVP + v1;
+            sl_ok0[k] = t < C32_TT && f0 + ch0 < p.F;
+            sl_ok1[k] = t < C32_TT && f0 + ch1 < p.F;
+        }
+    }
+    float4 pre[C32_SLOTS];
+    auto load_tile = [&](int tb) {
+        if (VEC) {
+            const int nt = min(C32_TT, t1 - tb);
+            const float2 *base = p.in + (long)tb * frame;
+#pragma unroll
+            for (int k = 0; k < C32_SLOTS; k++) {
+                pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sl_ok0[k] && sl_t[k] < nt) {
+                    if (sl_ok1[k]) pre[k] = __ldg(reinterpret_cast<const float4 *>(base + sl_g[k]));
+                    else {
+                        const float2 v = __ldg(base + sl_g[k]);
+                        pre[k] = make_float4(v.x, v.y, 0.f, 0.f);
+                    }
+                }
+            }
+        }
+    };
+    auto store_tile = [&](int tb, float2 *buf) {
+        const int nt = min(C32_TT, t1 - tb);
+        if (VEC) {
+#pragma unroll
+            for (int k = 0; k < C32_SLOTS; k++)
+                if (sl_t[k] < nt && sl_ok0[k]) {
+                    buf[sl_s0[k]] = make_float2(pre[k].x, pre[k].y);
+                    buf[sl_s1[k]] = make_float2(pre[k].z, pre[k].w);      // (a channel past F: zeros into its own row)
+                }
+        } else {
+            // scalar path (odd run lengths / unaligned rows): global [t][station][chan][pol] -> [t][chan][v]
+            for (int e = tid; e < nt * per_t; e += blockDim.x) {
+                const int t = e / per_t, r = e - t * per_t;
+                const int s = r / (CH * p.npol), q = r - s * (CH * p.npol);
+                const int ch = q / p.npol, pol = q - ch * p.npol;
+                float2 v = make_float2(0.f, 0.f);
+                if (f0 + ch < p.F) v = __ldg(p.in + (long)(tb + t) * frame + ((long)s * p.Fstride + p.f_off + f0 + ch) * p.npol + pol);
+                buf[(t * CH + ch) * NVP + s * p.npol + pol] = v;
+            }
+        }
+    };
+
+    __syncthreads();
+    load_tile(t0);
+    store_tile(t0, c32_smem);
+    int cur = 0;
+    for (int tb = t0; tb < t1; tb += C32_TT) {
+        const int nt = min(C32_TT, t1 - tb);
+        const bool more = tb + C32_TT < t1;
+        if (more) load_tile(tb + C32_TT);                       // the next tile's loads fly during this tile's FMAs
+        __syncthreads();                                        // tile `cur` is complete, tile `cur^1` is free
+        if (worker) {
+            const float2 *buf = c32_smem + cur * tile;
+            const float4 *row = reinterpret_cast<const float4 *>(buf + c * NVP + bi * 4);
+            const float4 *col = reinterpret_cast<const float4 *>(buf + c * NVP + bj * 4);
+            const int tstride = CH * NVP / 2;                   // float4 per time step
+#pragma unroll 4
+            for (int t = 0; t < nt; t++) {
+                const float4 r01 = row[t * tstride], r23 = row[t * tstride + 1];
+                const float4 c01 = col[t * tstride], c23 = col[t * tstride + 1];
+                const float2 a[4] = {make_float2(r01.x, r01.y), make_float2(r01.z, r01.w), make_float2(r23.x, r23.y), make_float2(r23.z, r23.w)};
+                const float2 bb[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y), make_float2(c23.z, c23.w)};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        // accum += a * conj(b) (cxmac, lib/clXEngine_impl.cc:729-736), four chained FMAs
+                        acc[i][j].x = fmaf(a[i].x, bb[j].x, acc[i][j].x);
+                        acc[i][j].x = fmaf(a[i].y, bb[j].y, acc[i][j].x);
+                        acc[i][j].y = fmaf(a[i].y, bb[j].x, acc[i][j].y);
+                        acc[i][j].y = fmaf(-a[i].x, bb[j].y, acc[i][j].y);
+                    }
+            }
+        }
+        if (more) store_tile(tb + C32_TT, c32_smem + (cur ^ 1) * tile);
+        cur ^= 1;
+    }
+    if (!worker || f0 + c >= p.F) return;
+    const int nbl = p.A * (p.A + 1) / 2, pp = p.npol * p.npol;
+    float2 *out = p.out + (long)slice * p.nout + (long)(f0 + c) * nbl * pp;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int v1 = bi * 4 + i, v2 = bj * 4 + j;
+            if (v1 >= p.NV || v2 >= p.NV) continue;
+            const int s1 = v1 / p.npol, p1 = v1 - s1 * p.npol, s2 = v2 / p.npol, p2 = v2 - s2 * p.npol;
+            if (s2 > s1) continue;
+            const long o = (long)(s1 * (s1 + 1) / 2 + s2) * pp + p1 * p.npol + p2;
+            float2 v = acc[i][j];
+            if (p.ts == 1 && p.accumulate) {
+                v.x += out[o].x;
+                v.y += out[o].y;
+            }
+            out[o] = v;
+        }
+}
+
+// partial matrices of the time slices, summed in slice order
+__global__ void k_c32_reduce(const float2 *__restrict__ part, float2 *__restrict__ out, long n, int ts, int accumulate)
+{
     const long stride = (long)gridDim.x * blockDim.x;
-    const long frame = (long)A * Fstride * npol;
-    for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
-        const int pp = (int)(o % (npol * npol));
-        const long fk = o / (npol * npol);
-        const int k = (int)(fk % nbl), f = (int)(fk / nbl);
-        int s1 = (int)(-0.5 + sqrt(0.25 + 2.0 * k));
-        while ((s1 + 1) * (s1 + 2) / 2 <= k) s1++;
-        while (s1 * (s1 + 1) / 2 > k) s1--;
-        const int s2 = k - s1 * (s1 + 1) / 2;
-        const int p1 = pp / npol, p2 = pp % npol;
-        const float2 *r = in + ((long)s1 * Fstride + f_off + f) * npol + p1;
-        const float2 *c = in + ((long)s2 * Fstride + f_off + f) * npol + p2;
-        float re = 0.f, im = 0.f;
-        for (int t = 0; t < T; t++) {
-            const float2 a = __ldg(r + t * frame), b = __ldg(c + t * frame);
-            re += a.x * b.x + a.y * b.y;
-            im += a.y * b.x - a.x * b.y;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float2 v = part[i];
+        for (int s = 1; s < ts; s++) {
+            v.x += part[s * n + i].x;
+            v.y += part[s * n + i].y;
         }
         if (accumulate) {
-            re += out[o].x;
-            im += out[o].y;
+            v.x += out[i].x;
+            v.y += out[i].y;
         }
-        out[o] = make_float2(re, im);
+        out[i] = v;
     }
 }
 
@@ -623,9 +778,51 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     const int sms = device_sm_count(x->device);
     if (x->data_type == CLB200_DTYPE_COMPLEX) {
         CLB_CHECK(out_f32 != nullptr, CLB200_EINVAL, "clXEngine: complex input has no integer output");
-        long total = x->out_items();
-        k_xengine_c32<<<grid_for((total + 127) / 128, sms, 16), 128, 0, st>>>(
-            (const float2 *)d_in, out_f32, x->A, x->npol, x->F, Fstride, f_off, T, accumulate);
+        XeC32 q;
+        q.in = (const float2 *)d_in;
+        q.A = x->A;
+        q.npol = x->npol;
+        q.NV = x->A * x->npol;
+        q.NB = (q.NV + 3) / 4;
+        q.nblk = q.NB * (q.NB + 1) / 2;
+        q.F = x->F;
+        q.Fstride = Fstride;
+        q.f_off = f_off;
+        q.T = T;
+        q.accumulate = accumulate;
+        q.nout = x->out_items();
+        CLB_CHECK(q.nblk <= 256, CLB200_EINVAL, "clXEngine: too many inputs for the complex kernel");
+        // channels per CTA: one thread per (channel, 4 x 4 block), at most 256 threads and 48 KiB of staged samples
+        int ch = std::min(std::min(256 / q.nblk, 384 / (q.NB * 4)), 32);
+        if (ch >= 4) ch &= ~3;
+        ch = std::max(1, std::min(ch, x->F));
+        q.ch = ch;
+        const int groups = (x->F + ch - 1) / ch;
+        const int threads = (ch * q.nblk + 31) / 32 * 32;
+        // enough CTAs for ~4 per SM: split the integration into time slices when there are few channel groups
+        int ts = std::max(1, std::min((4 * sms + groups - 1) / groups, (T + 4 * C32_TT - 1) / (4 * C32_TT)));
+        ts = std::min(ts, 64);
+        q.ts = ts;
+        if (ts > 1) {
+            CLB_TRY(x->d_acc.reserve((size_t)ts * q.nout * 8));
+            q.out = (float2 *)x->d_acc.p;
+        } else {
+            q.out = out_f32;
+        }
+        const size_t smem = 2 * (size_t)C32_TT * ch * q.NB * 4 * sizeof(float2);         // two staging buffers
+        // 16 B staging loads: whole float4 per (t, station) run, 16 B aligned rows, few enough slots per thread
+        const bool vec = (ch * x->npol) % 2 == 0 && ((long)Fstride * x->npol) % 2 == 0 && ((long)f_off * x->npol) % 2 == 0 &&
+                         ((uintptr_t)d_in % 16) == 0 && (ch % 2 == 0 || x->npol == 2) &&
+                         (long)C32_TT * x->A * (ch * x->npol / 2) <= (long)C32_SLOTS * threads;
+        if (vec) k_xengine_c32_tiled<true><<<dim3(groups, ts), threads, smem, st>>>(q);
+        else k_xengine_c32_tiled<false><<<dim3(groups, ts), threads, smem, st>>>(q);
+        CLB_CUDA(cudaGetLastError());
+        x->n_launch++;
+        if (ts > 1) {
+            k_c32_reduce<<<grid_for((q.nout + 255) / 256, sms, 8), 256, 0, st>>>((const float2 *)x->d_acc.p, out_f32, q.nout, ts,
+                                                                               accumulate);
+            x->n_launch++;
+        }
         CLB_CUDA(cudaGetLastError());
         x->n_launch++;
         return CLB200_OK;

@@ -399,6 +399,24 @@ def test_xengine_accumulate_and_complex_and_packed():
     assert np.array_equal(got, orc.xengine_exact(orc.unpack4(packed), A, F, T, npol))
 
 
+@pytest.mark.parametrize("A,F,T,npol", [(2, 1, 1, 1), (3, 17, 33, 1), (5, 4, 33, 2), (32, 64, 256, 1), (16, 33, 100, 2),
+                                         (64, 5, 64, 1), (32, 7, 2048, 1), (9, 40, 50, 1), (32, 3, 16, 2), (32, 1024, 32, 1)])
+def test_xengine_complex_float_tiled_kernel(A, F, T, npol):
+    """DTYPE_COMPLEX (the reference's default): register-tiled FP32 kernel, time slices summed in a fixed order;
+    against the oracle's reference-order float loop (lib/clXEngine_impl.cc:739-810), incl. accumulate and shards"""
+    xc = orc.rng_c32(T * A * F * npol, orc.SEED_X + 70)
+    blk = _xe(capi.DTYPE_COMPLEX, npol, A, F, T)
+    want = orc.xengine_f32(xc, A, F, T, npol)
+    got = blk.work(xc)
+    assert rel_err(got, want) < TOL
+    assert np.array_equal(blk.work(xc), got)                     # deterministic
+    assert rel_err(blk.work(xc, accumulate=True, out=got.copy()), 2 * want) < TOL
+    if F >= 4:
+        sh = _xe(capi.DTYPE_COMPLEX, npol, A, F // 2, T)
+        sh.set_shard(F, F - F // 2)
+        assert rel_err(sh.work(xc), want.reshape(F, -1)[F - F // 2:].reshape(-1)) < TOL
+
+
 def test_xengine_channel_shard_matches_full():
     A, F, T = 8, 64, 128
     buf = orc.rng_i8(T * A * F * 2, orc.SEED_X + 5)

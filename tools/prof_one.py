@@ -1,4 +1,4 @@
-"""Launches one block's device-resident kernel a few times (for ncu).  usage: prof_one.py fft|xengine|filter|pfb|fir [variant]"""
+"""Launches one block's device-resident kernel a few times (for ncu).  usage: prof_one.py fft|xengine|xengine_batch|xengine_c32|filter|pfb|fir [variant]"""
 import os
 import sys
 
@@ -46,5 +46,20 @@ elif what == "pfb":
     blk = blocks.clPolyphaseChannelizer(*gpu, taps, 65536, 64, 64, list(range(64)))
     for _ in range(reps):
         blk.launch_device(x.data_ptr(), y.data_ptr(), (n - 128) // 64, sp)
+elif what == "xengine_batch":
+    A, F, T, K = 32, 1024, 1024, 16
+    per = T * A * F * 2
+    buf = torch.randint(-127, 128, (per * K,), dtype=torch.int8, device="cuda")
+    vis = torch.empty(K * F * (A * (A + 1) // 2) * 2, dtype=torch.float32, device="cuda")
+    blk = blocks.clXEngine(*gpu, False, capi.DTYPE_BYTE, 1, A, 1, 0, F, T, [])
+    for i in range(reps):
+        blk.launch_device_batch(buf.data_ptr(), vis.data_ptr(), K, sp)
+elif what == "xengine_c32":
+    A, F, T = 32, 256, 1024
+    xc = torch.empty(T * A * F * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
+    vis = torch.empty(F * (A * (A + 1) // 2) * 2, dtype=torch.float32, device="cuda")
+    blk = blocks.clXEngine(*gpu, False, capi.DTYPE_COMPLEX, 1, A, 1, 0, F, T, [])
+    for i in range(reps):
+        blk.launch_device(xc.data_ptr(), vis.data_ptr(), False, sp)
 torch.cuda.synchronize()
 print("done", what)
