@@ -102,6 +102,7 @@ struct clb200_block {
 namespace clb200 {
 
 bool is_pinned(const void *p);
+void pinned_cache_clear();
 size_t small_call_bytes();
 
 struct PortDesc {

@@ -1,6 +1,7 @@
 // runtime.cu -- device selection, buffers, error state, handle lifetime.
 // Replaces GRCLBase::InitOpenCL / cleanup (lib/GRCLBase.cpp:17-369, :423-483).
 #include "common.cuh"
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 
@@ -79,14 +80,30 @@ void Buf::release()
     cap = 0;
 }
 
+// Scheduler-sized calls come thousands of times per second on the same few (pageable) buffers, and
+// cudaPointerGetAttributes costs ~0.5 us per port: pages that were seen to be PAGEABLE are remembered in a small
+// direct-mapped table (a stale "pageable" only costs the staging copy; page-locked pointers are always re-checked,
+// so a buffer that was freed or unregistered is never handed to a kernel).  register / unregister clear the table.
+static std::atomic<uintptr_t> g_pageable[256];
+
+void pinned_cache_clear()
+{
+    for (auto &e : g_pageable) e.store(0, std::memory_order_relaxed);
+}
+
 bool is_pinned(const void *p)
 {
+    const uintptr_t page = (uintptr_t)p >> 12;
+    std::atomic<uintptr_t> &slot = g_pageable[page & 255];
+    if (slot.load(std::memory_order_relaxed) == page) return false;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
-    return a.type == cudaMemoryTypeHost;
+    if (a.type == cudaMemoryTypeHost) return true;
+    slot.store(page, std::memory_order_relaxed);
+    return false;
 }
 
 } // namespace clb200
@@ -189,6 +206,7 @@ int clb200_register_host_buffer(void *ptr, size_t bytes)
 {
     CLB_CHECK(ptr != nullptr && bytes > 0, CLB200_EINVAL, "bad host range");
     CLB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    pinned_cache_clear();
     return CLB200_OK;
 }
 
@@ -196,6 +214,7 @@ int clb200_unregister_host_buffer(void *ptr)
 {
     CLB_CHECK(ptr != nullptr, CLB200_EINVAL, "null pointer");
     CLB_CUDA(cudaHostUnregister(ptr));
+    pinned_cache_clear();
     return CLB200_OK;
 }
 
