@@ -160,6 +160,7 @@ public:
     static sptr make(int openclPlatform, int devSelector, int platformId, int devId, int decimation,
                      const std::vector<gr_complex> &taps, int nthreads = 1, int setDebug = 0);
     virtual void set_taps2(const std::vector<gr_complex> &taps) = 0;
+    virtual std::vector<gr_complex> taps() const = 0;
 };
 
 // include/clenabled/clQuadratureDemod.h:49

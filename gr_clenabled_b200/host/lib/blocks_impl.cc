@@ -585,6 +585,7 @@ public:
 // --------------------------------------------------------------- clComplexFilter --
 class clComplexFilter_impl : public clComplexFilter
 {
+    std::vector<gr_complex> d_taps;
     Handle d;
 
 public:
@@ -592,7 +593,8 @@ public:
 
     clComplexFilter_impl(int dev, int decimation, const std::vector<gr_complex> &taps)
         : gr::sync_decimator("clComplexFilter", gr::io_signature::make(1, 1, sizeof(gr_complex)),
-                             gr::io_signature::make(1, 1, sizeof(gr_complex)), decimation)
+                             gr::io_signature::make(1, 1, sizeof(gr_complex)), decimation),
+          d_taps(taps)
     {
         must(clb200_cfilter_create(dev, decimation, reinterpret_cast<const float *>(taps.data()), (int)taps.size(), &d.h));
         // history lives in the handle (see clFilter_impl above): in[0] is the first NEW sample
@@ -601,7 +603,9 @@ public:
     {
         if (clb200_cfilter_set_taps(d.h, reinterpret_cast<const float *>(taps.data()), (int)taps.size()) != CLB200_OK)
             throw std::invalid_argument(clb200_last_error());
+        d_taps = taps;
     }
+    std::vector<gr_complex> taps() const override { return d_taps; }
     int work(int noutput_items, gr_vector_const_void_star &in, gr_vector_void_star &out) override
     {
         long n_out = 0;

@@ -34,6 +34,19 @@ def enum_values(yml, param_id, attr):
     raise KeyError((yml, param_id))
 
 
+PYBIND_CLASSES = ["clMathConst", "clMathOp", "clLog", "clSNR", "clComplexToMag", "clComplexToArg", "clComplexToMagPhase",
+                  "clMagPhaseToComplex", "clFFT", "clFilter", "clPolyphaseChannelizer", "clXEngine", "clXCorrelate",
+                  "clxcorrelate_fft_vcf", "clComplexFilter", "clQuadratureDemod", "clSignalSource"]
+
+
+def pybind_init_args(cls):
+    """keyword names of the constructor as python/bindings/<cls>_python.cc binds them, in order"""
+    text = open(os.path.join(REF, "python", "bindings", cls + "_python.cc")).read()
+    init = text[text.index("py::init("):]
+    init = init[:init.index("D(" + cls + ",make)")] if ("D(" + cls + ",make)") in init else init[:init.index(")\n\n")]
+    return re.findall(r'py::arg\("(\w+)"\)', init)
+
+
 def main():
     inc = os.path.join(REF, "include", "clenabled")
     out = {
@@ -45,6 +58,8 @@ def main():
             "clenabled_clMultConst.type.datatype": enum_values(os.path.join(REF, "grc", "clenabled_clMultConst.block.yml"), "type", "datatype"),
         },
     }
+    out["pybind_module"] = "clenabled_python"
+    out["pybind_init_args"] = {c: pybind_init_args(c) for c in PYBIND_CLASSES}
     with open(os.path.join(HERE, "ref_constants.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
         f.write("\n")

@@ -233,6 +233,44 @@ def test_filter_matches_reference_overlap_add(golden):
     assert blocks.filter_ref_sizes(256) == (512, 257)
 
 
+@pytest.mark.parametrize("use_time", [False, True])
+def test_filter_set_taps2_from_another_thread_while_work_runs(use_time):
+    """set_taps2 is called from another thread than work() in a flowgraph (reference: d_setlock,
+    lib/clFilter_impl.cc:774-789): every work() call must run with ONE consistent tap set, old or new"""
+    import threading
+    K, L = 200, 4096
+    ta = (orc.rng_f32(K, 31) / K).astype(np.float32)
+    tb = (orc.rng_f32(K, 32) / K + 0.01).astype(np.float32)
+    sa, sb = float(np.sum(ta.astype(np.float64))), float(np.sum(tb.astype(np.float64)))
+    blk = blocks.clFilter(*GPU, 1, ta, 1, 0, use_time)
+    x = np.ones(L, c64)
+    stop, errors, seen = threading.Event(), [], set()
+
+    def setter():
+        i = 0
+        while not stop.is_set():
+            blk.set_taps2(tb if i % 2 == 0 else ta)
+            i += 1
+
+    th = threading.Thread(target=setter)
+    th.start()
+    try:
+        for _ in range(300):
+            y = blk.work(x)
+            tail = y[K:]                                       # past the history: DC gain of the active tap set
+            if np.allclose(tail, sa, atol=1e-4):
+                seen.add("a")
+            elif np.allclose(tail, sb, atol=1e-4):
+                seen.add("b")
+            else:
+                errors.append((float(tail.real.min()), float(tail.real.max())))
+    finally:
+        stop.set()
+        th.join()
+    assert not errors, errors[:3]
+    assert seen == {"a", "b"}
+
+
 @pytest.mark.parametrize("name", ["lp256_d1", "lp256_d4", "ramp256_d1", "short37_d3", "one_tap"])
 def test_filter_matches_reference_build_vectors(golden, name):
     """the CUDA clFilter (both modes) against outputs of the reference's OWN fft_filter_ccf / fir_filter_ccf
