@@ -82,6 +82,10 @@ struct XeGatherSync {
     int nranks, signal, wait;
 };
 
+// CTA-wide barrier of k_xengine_i8: every warp reaches it at the same program location (the warp shares differ only
+// inside the MMA / epilogue sections of xe_body), as compute-sanitizer's synccheck requires
+__device__ __forceinline__ void xe_cta_sync() { __syncthreads(); }
+
 // which row tiles warp share Q of WPC owns
 template <int WPC, int Q>
 __host__ __device__ constexpr bool owns(int mi)
@@ -107,12 +111,29 @@ __host__ __device__ constexpr int mi_max()
 }
 
 // MT: row tiles (8 inputs each) per channel; WPC: warps sharing one channel; FC = 16/WPC
-template <int MT, int WPC, int Q, int NPOL>
-__device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
+template <int MT, int WPC>
+__host__ __device__ constexpr int nt_max()                   // most accumulator tiles any warp share owns
+{
+    int mx = 0;
+    for (int q = 0; q < WPC; q++) {
+        int n = 0;
+        for (int m = 0; m < MT; m++) {
+            const int r = m % (2 * WPC);
+            if (r == q || r == 2 * WPC - 1 - q) n += m + 1;
+        }
+        if (n > mx) mx = n;
+    }
+    return mx;
+}
+
+// One body for every warp share: the barriers sit in code all warps run; only the MMA and epilogue sections
+// branch on the warp's share q (compile-time tile sets inside each branch).
+template <int MT, int WPC, int NPOL>
+__device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf, const int q)
 {
     constexpr int FC = XE_WARPS / WPC;
-    constexpr int NT = tile_base<MT, WPC, Q>(MT);            // accumulator tiles of this warp
-    constexpr int MMAX = mi_max<MT, WPC, Q>();
+    constexpr int NT = nt_max<MT, WPC>();                    // accumulator tiles (the largest share's)
+    constexpr int MMAX = MT - 1;
     constexpr int CSW = MT * 16 * XE_RSW + 2;                // channel stride (words), = 2 mod 32
     constexpr int ZW = FC * CSW;                             // words per stage buffer
     constexpr int NVP = MT * 8;
@@ -252,7 +273,7 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
     load_stage(s0);
     store_stage(zbuf);
     if (s0 + 1 < s1) load_stage(s0 + 1);
-    __syncthreads();
+    xe_cta_sync();
 
     for (int sg = s0; sg < s1; sg++) {
         {
@@ -267,16 +288,20 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                     a[m][2] = (int)r[4];
                     a[m][3] = (int)r[8 * XE_RSW + 4];
                 }
-                static_for<0, MT>([&](auto mi_) {
-                    constexpr int mi = decltype(mi_)::value;
-                    if constexpr (owns<WPC, Q>(mi)) {
-                        constexpr int tb = tile_base<MT, WPC, Q>(mi);
-                        static_for<0, mi + 1>([&](auto nj_) {
-                            constexpr int nj = decltype(nj_)::value;
-                            mma_s8(acc[tb + nj][0], a[mi], a[nj][0], a[nj][2]);   // columns = re rows of tile nj
-                            mma_s8(acc[tb + nj][1], a[mi], a[nj][1], a[nj][3]);   // columns = im rows
-                        });
-                    }
+                static_for<0, WPC>([&](auto q_) {
+                    constexpr int Q = decltype(q_)::value;
+                    if (q != Q) return;
+                    static_for<0, MT>([&](auto mi_) {
+                        constexpr int mi = decltype(mi_)::value;
+                        if constexpr (owns<WPC, Q>(mi)) {
+                            constexpr int tb = tile_base<MT, WPC, Q>(mi);
+                            static_for<0, mi + 1>([&](auto nj_) {
+                                constexpr int nj = decltype(nj_)::value;
+                                mma_s8(acc[tb + nj][0], a[mi], a[nj][0], a[nj][2]);   // columns = re rows of tile nj
+                                mma_s8(acc[tb + nj][1], a[mi], a[nj][1], a[nj][3]);   // columns = im rows
+                            });
+                        }
+                    });
                 });
             }
             // feed: next stage into the other Z buffer, the one after it into registers
@@ -288,7 +313,7 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
         const int grp = sg / nst;
         const bool group_done = (sg + 1 == s1) || ((sg + 1) % nst == 0);
         if (!group_done) {
-            __syncthreads();
+            xe_cta_sync();
             continue;
         }
         const int f0 = grp * FC;
@@ -302,6 +327,9 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
         const int f = f0 + chl;
         if constexpr (NT > 0) {
             if (f < p.F) {
+              static_for<0, WPC>([&](auto q_) {
+                constexpr int Q = decltype(q_)::value;
+                if (q != Q) return;
                 static_for<0, MT>([&](auto mi_) {
                     constexpr int mi = decltype(mi_)::value;
                     if constexpr (owns<WPC, Q>(mi)) {
@@ -350,10 +378,11 @@ __device__ __forceinline__ void xe_body(const XeParams &p, uint32_t *zbuf)
                         });
                     }
                 });
+              });
             }
         }
         zero_acc();
-        __syncthreads();
+        xe_cta_sync();
     }
 }
 
@@ -361,16 +390,7 @@ template <int MT, int WPC, int NPOL>
 __global__ void __launch_bounds__(XE_THREADS, 1) k_xengine_i8(XeParams p)
 {
     extern __shared__ __align__(16) uint32_t xe_smem[];
-    if constexpr (WPC == 1) {
-        xe_body<MT, 1, 0, NPOL>(p, xe_smem);
-    } else {
-        // every warp share runs the same barrier sequence; only the tile sets differ
-        const int q = (threadIdx.x >> 5) % WPC;
-        static_for<0, WPC>([&](auto q_) {
-            constexpr int Q = decltype(q_)::value;
-            if (q == Q) xe_body<MT, WPC, Q, NPOL>(p, xe_smem);
-        });
-    }
+    xe_body<MT, WPC, NPOL>(p, xe_smem, (threadIdx.x >> 5) % WPC);
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem()
