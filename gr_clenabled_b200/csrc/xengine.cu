@@ -705,6 +705,7 @@ struct XEngine : clb200_block {
     const XeVariant *var = nullptr;
     bool use_tc = false;
     bool use_tma = false;              // TMA-fed variant of the tcgen05 kernel (needs 16 B aligned rows)
+    bool use_tma_pk = false;           // ... and its packed 4-bit variant
     int l2promo = 0;
     void *gather[8] = {};              // full matrices of every rank (clb200_xengine_set_gather)
     int ngather = 0;
@@ -849,7 +850,16 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     }
     const int8_t *src = (const int8_t *)d_in;
     float scale = 1.0f / (127.0f * 127.0f);
+    // packed 4 bit: the TMA kernel expands the nibbles in its transpose stage when the packed rows are 16 B aligned
+    // (and one sample lane run is >= 16 B: 16 channels per CTA); otherwise a separate pass unpacks into int8 pairs
+    bool pk = false;
     if (x->data_type == CLB200_DTYPE_PACKEDXY) {
+        pk = x->use_tc && x->use_tma && x->use_tma_pk && ((uintptr_t)d_in % 16 == 0) &&
+             (((long)Fstride * x->npol) % 16 == 0) && ((uintptr_t)out_i32 % 8 == 0) && ((uintptr_t)out_f32 % 8 == 0) &&
+             (((long)f_off * x->npol) % 16 == 0) && nbatch == 1;
+        scale = 1.0f / 49.0f;
+    }
+    if (x->data_type == CLB200_DTYPE_PACKEDXY && !pk) {
         long n = (long)T * x->A * Fstride * x->npol;
         CLB_TRY(x->d_unpacked.reserve((size_t)n * 2));
         k_unpack4<<<grid_for((n + 255) / 256, sms, 8), 256, 0, st>>>((const uint8_t *)d_in,
@@ -857,12 +867,11 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         CLB_CUDA(cudaGetLastError());
         x->n_launch++;
         src = (const int8_t *)x->d_unpacked.p;
-        scale = 1.0f / 49.0f;
     }
     const XeVariant *v = x->var;
     const bool tc = x->use_tc;                         // tcgen05/TMEM kernel (<= 32 rows of inputs)
     const long nout = x->out_items();
-    long rowb = (long)Fstride * x->npol * 2;
+    long rowb = (long)Fstride * x->npol * (pk ? 1 : 2);
     const bool tma_ok = tc && x->use_tma && ((uintptr_t)src % 16 == 0) && (rowb % 16 == 0) &&
                         ((uintptr_t)out_i32 % 8 == 0) && ((uintptr_t)out_f32 % 8 == 0);
     // TMA kernel: 8 channels per CTA while 16 would leave SMs without a channel group (then no CTA
@@ -898,8 +907,13 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
             fc = 8;
             want_slices = 1;
         }
-        if (nbatch > 1) fc = 16;                         // persistent over (integration, group): the widest rows
-        if (x->fc_override == 8 || x->fc_override == 16) {
+        if (nbatch > 1 || pk) fc = 16;                   // persistent over (integration, group): the widest rows; packed: >= 16 B runs
+        if (pk && want_slices > 0) {                     // the slice count that goes with 16 channels
+            const int ng = (x->F + 15) / 16, nstc = (T + 31) / 32;
+            want_slices = 1;
+            while (want_slices * 2 <= 4 && want_slices * 2 <= nstc && (long)ng * want_slices * 2 <= sms) want_slices *= 2;
+        }
+        if ((x->fc_override == 8 || x->fc_override == 16) && !pk) {
             fc = x->fc_override;
             want_slices = -1;
         }
@@ -938,7 +952,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         if (bg > 0) grid = std::min(bg, ngroups * nbatch);
     }
     CUtensorMap tmap;
-    const bool tma = tma_ok && tm_make_map(&tmap, src, rowb, x->A, T, x->npol, fc, x->l2promo, nbatch);
+    const bool tma = tma_ok && tm_make_map(&tmap, src, rowb, x->A, T, x->npol, fc, x->l2promo, nbatch, pk);
     CLB_CHECK(tma || nbatch == 1, CLB200_ESTATE, "clXEngine: batched launches need the TMA kernel");
     CLB_CHECK(tma || !tma_ok, CLB200_ECUDA, "clXEngine: cuTensorMapEncodeTiled failed");
     // TMA kernel, time-sliced: the slices of a channel group form a thread-block cluster and meet
@@ -1017,7 +1031,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = x->pdl ? 2 : 1;
-        CLB_CUDA(cudaLaunchKernelEx(&cfg, tm_kernel(x->npol, fc), p, tmap));
+        CLB_CUDA(cudaLaunchKernelEx(&cfg, tm_kernel(x->npol, fc, pk), p, tmap));
     } else if (tc) {
         if (x->npol == 1) k_xengine_tc<1><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
         else k_xengine_tc<2><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
@@ -1374,6 +1388,9 @@ int clb200_xengine_create(int device, int data_type, int npol, int num_inputs, i
                 e2 = cudaFuncSetAttribute((const void *)tm_kernel(npol, 16),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM);
             x->use_tma = (e2 == cudaSuccess) && tm_encoder() != nullptr;
+            const char *up = getenv("CLB200_XE_UNPACK_PASS");       // 1: keep the separate unpack pass (A/B measurements)
+            x->use_tma_pk = x->use_tma && !(up && atoi(up)) && cudaFuncSetAttribute((const void *)tm_kernel(npol, 16, true),
+                                                               cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM) == cudaSuccess;
             const char *fo = getenv("CLB200_XE_FC");
             x->fc_override = fo ? atoi(fo) : 0;
             const char *pd = getenv("CLB200_XE_PDL");

@@ -260,22 +260,36 @@ __device__ __forceinline__ void tm_write_out(const XeParams &p, const int2 *stg,
     }
 }
 
+// packed 4-bit samples (hi nibble re, lo nibble im; CharToComplex LUT lib/clXEngine_impl.cc:833: 4-bit two's complement
+// with -8 read as 0): 4 time steps of one sample lane -> the 4 re bytes and the 4 im bytes, SIMD within a register
+__device__ __forceinline__ uint32_t tm_nib4(uint32_t n)          // n: four nibbles 0..15, one per byte
+{
+    const uint32_t z = n ^ 0x08080808u;                               // 0 exactly where the nibble is 8
+    const uint32_t r = ((z | 0x80808080u) - 0x08080808u) ^ 0x80808080u;   // per byte (n ^ 8) - 8 = sign extension
+    const uint32_t nz = (((z + 0x7F7F7F7Fu) | z) >> 7) & 0x01010101u;     // 1 where z != 0
+    return r & (nz * 0xFFu);
+}
+
 // FC = channels per CTA: 16 fills the 512 TMEM columns; 8 (256 columns) lets 1024 channels spread over
 // 128 CTAs WITHOUT slicing time, i.e. without any cross-CTA reduction.  A raw box is always 32 KiB:
 // KT = 512 / FC time steps (KS = KT / 32 MMA k-steps per stage).
-template <int NPOL, int FC>
+// PK: the input is packed 4 bit (one byte per sample): the boxes are half as large and the transpose stage expands the
+// nibbles between ldmatrix and stmatrix (one load -> a re and an im store), so packed data crosses HBM once, as 1 B/sample.
+template <int NPOL, int FC, bool PK = false>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
 {
-    constexpr int IB = FC * NPOL * 2;                        // bytes per (t, station) run: 16 | 32 | 64
+    constexpr int IB = FC * NPOL * (PK ? 1 : 2);             // bytes per (t, station) run: 16 | 32 | 64
     constexpr int NH = IB / 16;                              // 16 B chunks per run
     constexpr int KT = 512 / FC;                             // time steps per stage
     constexpr int KS = KT / 32;                              // MMA k-steps per stage
     constexpr int ASTN = 32 / NPOL;                          // stations per box
     constexpr int CSK = KS * 2048 + ((NPOL == 1) ? 32 : 64); // channel image stride: the skew spreads the STSM banks
-    constexpr int UPW = 64 / XE_WARPS;                       // ldmatrix.x2 units per warp and stage
+    constexpr int RAWB = ASTN * KT * IB;                     // bytes per raw box: 32 KiB (16 KiB packed)
+    constexpr int UNITS = RAWB / 512;                        // ldmatrix.x2 units per stage
+    constexpr int UPW = UNITS / XE_WARPS;                    // ... per warp
     static_assert(FC * CSK <= TM_IMGB, "stage image does not fit");
-    static_assert(ASTN * KT * IB == TM_RAWB, "raw box is 32 KiB");
+    static_assert(RAWB <= TM_RAWB && IB >= 16 && UPW >= 1, "raw box shape");
 
     extern __shared__ uint8_t tm_smem_raw[];
     // the swizzle pattern is a function of the shared-memory ADDRESS: align the ring to 1 KiB
@@ -382,8 +396,8 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
             for (int n = 0; n < nstages; n++) {
                 const int r = n % TM_NR;
                 if (n >= TM_NR) tc_mbar_wait(&rempty[r], (uint32_t)(n / TM_NR - 1) & 1u);
-                tm_expect_tx(&rfull[r], TM_RAWB);
-                tm_load_4d(raw_addr + r * TM_RAWB, &tmap, &rfull[r], (p.f_off + grp * FC) * NPOL * 2, st * KT, 0, kl);
+                tm_expect_tx(&rfull[r], RAWB);
+                tm_load_4d(raw_addr + r * TM_RAWB, &tmap, &rfull[r], (p.f_off + grp * FC) * NPOL * (PK ? 1 : 2), st * KT, 0, kl);
                 if (++st == nst) {
                     st = 0;
                     if (strided) {
@@ -438,7 +452,7 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
         for (int i = 0; i < UPW; i++) {
             const int u = warp * UPW + i;
-            constexpr int UPS = 64 / ASTN;                       // units per station
+            constexpr int UPS = UNITS / ASTN;                    // units per station
             const int s = u / UPS, w = u % UPS;
             const int kc0 = (NH == 1) ? 2 * w : w / (NH / 2 > 0 ? NH / 2 : 1);
             const int h0 = (NH == 1) ? 0 : 2 * (w % (NH / 2 > 0 ? NH / 2 : 1));
@@ -454,9 +468,10 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
                 const int q = lane >> 3, rr = lane & 7, mi = q >> 1;
                 const int kc = (NH == 1) ? kc0 + mi : kc0, h = (NH == 1) ? 0 : h0 + mi;
                 const int B = h * 16 + (q & 1) * 8 + rr;                 // byte of the (t, station) run
-                const int f = (NPOL == 1) ? (B >> 1) : (B >> 2);
-                const int v = (NPOL == 1) ? s : 2 * s + ((B >> 1) & 1);
-                const int m = 2 * v + (B & 1);
+                // unpacked: byte = (channel, pol, re|im); packed: byte = (channel, pol), its re row (im row = +16 B)
+                const int f = PK ? ((NPOL == 1) ? B : (B >> 1)) : ((NPOL == 1) ? (B >> 1) : (B >> 2));
+                const int v = PK ? ((NPOL == 1) ? s : 2 * s + (B & 1)) : ((NPOL == 1) ? s : 2 * s + ((B >> 1) & 1));
+                const int m = PK ? 2 * v : 2 * v + (B & 1);
                 st_off[i] = (uint32_t)(f * CS + (kc >> 1) * 2048 + (m >> 3) * 256 + (kc & 1) * 128 + (m & 7) * 16);
             }
         }
@@ -471,8 +486,22 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
                     uint32_t v[UPW][4];
 #pragma unroll
                     for (int i = 0; i < UPW; i++) tm_ldsm_t8(src + ld_off[i], v[i]);
+                    if constexpr (PK) {
 #pragma unroll
-                    for (int i = 0; i < UPW; i++) tm_stsm(dst + st_off[i], v[i]);
+                        for (int i = 0; i < UPW; i++) {
+                            uint32_t re[4], im[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                re[k] = tm_nib4((v[i][k] >> 4) & 0x0F0F0F0Fu);
+                                im[k] = tm_nib4(v[i][k] & 0x0F0F0F0Fu);
+                            }
+                            tm_stsm(dst + st_off[i], re);
+                            tm_stsm(dst + st_off[i] + 16, im);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < UPW; i++) tm_stsm(dst + st_off[i], v[i]);
+                    }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -615,8 +644,9 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
 }
 
 typedef void (*tm_kernel_t)(XeParams, const CUtensorMap);
-inline tm_kernel_t tm_kernel(int npol, int fc)
+inline tm_kernel_t tm_kernel(int npol, int fc, bool packed = false)
 {
+    if (packed) return npol == 1 ? &k_xengine_tma<1, 16, true> : &k_xengine_tma<2, 16, true>;
     if (npol == 1) return fc == 8 ? &k_xengine_tma<1, 8> : &k_xengine_tma<1, 16>;
     return fc == 8 ? &k_xengine_tma<2, 8> : &k_xengine_tma<2, 16>;
 }
@@ -639,13 +669,14 @@ inline tm_encode_fn tm_encoder()
 }
 // dims (innermost first): row bytes | time (stride A*rowb) | station (stride rowb) | integration of a batch (stride
 // T*A*rowb); box IB x KT x ASTN x 1.  Whatever a box covers beyond a dimension is zero-filled, per dimension.
-inline bool tm_make_map(CUtensorMap *tm, const void *base, long rowb, int A, int T, int npol, int fc, int l2promo, int nbatch)
+inline bool tm_make_map(CUtensorMap *tm, const void *base, long rowb, int A, int T, int npol, int fc, int l2promo, int nbatch,
+                        bool packed = false)
 {
     tm_encode_fn enc = tm_encoder();
     if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)rowb, (cuuint64_t)T, (cuuint64_t)A, (cuuint64_t)nbatch};
     const cuuint64_t strides[3] = {(cuuint64_t)rowb * A, (cuuint64_t)rowb, (cuuint64_t)rowb * A * T};
-    const int ib = fc * npol * 2;
+    const int ib = fc * npol * (packed ? 1 : 2);
     const cuuint32_t box[4] = {(cuuint32_t)ib, (cuuint32_t)(512 / fc), (cuuint32_t)(32 / npol), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides, box, estr,

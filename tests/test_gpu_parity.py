@@ -455,6 +455,29 @@ def test_xengine_complex_float_tiled_kernel(A, F, T, npol):
         assert rel_err(sh.work(xc), want.reshape(F, -1)[F - F // 2:].reshape(-1)) < TOL
 
 
+@pytest.mark.parametrize("A,F,T,npol", [(16, 64, 128, 2), (32, 32, 100, 1), (12, 40, 77, 2), (16, 24, 64, 2), (16, 16, 512, 2),
+                                         (16, 1024, 64, 2), (5, 48, 33, 1), (16, 2400, 32, 2)])
+def test_xengine_packed_4bit_fused_unpack_bit_exact(A, F, T, npol, monkeypatch):
+    """DTYPE_PACKEDXY with 16 B aligned packed rows: the TMA kernel expands the nibbles in its transpose stage (no
+    separate unpack pass); every byte pattern, ragged shapes, 1 / 2 / 4 time slices; the separate-pass route
+    (CLB200_XE_UNPACK_PASS=1) gives the same integers"""
+    packed = orc.rng_i8(T * A * F * npol, orc.SEED_X + 80).view(np.uint8)
+    packed[:256] = np.arange(256, dtype=np.uint8)                # every (re, im) nibble pair, incl. the -8 -> 0 entries
+    want = orc.xengine_exact(orc.unpack4(packed), A, F, T, npol)
+    blk = _xe(capi.DTYPE_PACKEDXY, npol, A, F, T)
+    l0 = blk.counters()["launches"]
+    got = blk.work_i32(packed)
+    assert np.array_equal(got, want)
+    fused_launches = blk.counters()["launches"] - l0
+    monkeypatch.setenv("CLB200_XE_UNPACK_PASS", "1")
+    blk2 = _xe(capi.DTYPE_PACKEDXY, npol, A, F, T)
+    l0 = blk2.counters()["launches"]
+    assert np.array_equal(blk2.work_i32(packed), want)
+    assert blk2.counters()["launches"] - l0 > fused_launches      # the unpack kernel ran only on the second route
+    vis = blk.work(packed)
+    assert rel_err(vis, (want[:, 0] + 1j * want[:, 1]) / 49.0) < 1e-6
+
+
 def test_xengine_channel_shard_matches_full():
     A, F, T = 8, 64, 128
     buf = orc.rng_i8(T * A * F * 2, orc.SEED_X + 5)
