@@ -1,8 +1,9 @@
 """Turn the ncu reports / launch list that tools/run_prof.sh left in gpurun_out/ into the tracked summaries under
-profiles/ (round-1 names).  usage: python tools/make_profiles.py"""
+profiles/ (names per round: ROUND=r2 by default).  usage: [ROUND=r2] python tools/make_profiles.py"""
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PRO = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+R = os.environ.get("ROUND", "r2")
 
 def summary(rep, dst):
     p = os.path.join(OUT, rep)
@@ -46,21 +47,28 @@ def launches():
              "kernel | launches | total us | share"]
     for k, v in tot.most_common():
         lines.append("%-70s %5d %12.1f %5.1f%%" % (k[:70], cnt[k], v, 100 * v / s))
-    open(os.path.join(PRO, "r1_launches_summary.txt"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(PRO, R + "_launches_summary.txt"), "w").write("\n".join(lines) + "\n")
     import shutil
-    shutil.copy(p, os.path.join(PRO, "r1_launches_bench.csv"))
+    shutil.copy(p, os.path.join(PRO, R + "_launches_bench.csv"))
 
 launches()
-tj = os.path.join(PRO, "r1_traffic.json")
-d = json.load(open(tj))
-for rep, dst, key, alg in (("fft.ncu-rep", "r1_fft8192_full.txt", "k_fft_8192pt_x8192vec", 1073741824),
-                           ("fftfilt.ncu-rep", "r1_fftfilt_full.txt", "k_fftfilt_256tap_64Mi", 1073741824),
-                           ("pfb.ncu-rep", "r1_pfb_full.txt", "k_pfb_64ch_64Mi", 1073741824),
-                           ("xe_tma.ncu-rep", "r1_xengine_full.txt", "k_xengine_tma_32st_1024ch_1024t", 71434240)):
-    b = summary(rep, dst)
+tj = os.path.join(PRO, R + "_traffic.json")
+d = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures in this directory "
+                 "(%s_*_full.txt); bench.py copies the clFFT figure into roofline.traffic when its launch shape matches" % R}
+XE = 32 * 1024 * 1024 * 2 + 1024 * 528 * 8
+for rep, dst, key, alg in (("fft.ncu-rep", "fft8192_full.txt", "k_fft_8192pt_x8192vec", 1073741824),
+                           ("fftfilt.ncu-rep", "fftfilt_full.txt", "k_fftfilt_256tap_64Mi", 1073741824),
+                           ("fir.ncu-rep", "fir_full.txt", "k_fir_256tap_64Mi", 1073741824),
+                           ("pfb.ncu-rep", "pfb_full.txt", "k_pfb_64ch_64Mi", 1073741824),
+                           ("xe_tma.ncu-rep", "xengine_full.txt", "k_xengine_tma_32st_1024ch_1024t", XE),
+                           ("xe_batch.ncu-rep", "xengine_batch16_full.txt", "k_xengine_tma_batch16_32st_1024ch_1024t", 16 * XE),
+                           ("xe_c32.ncu-rep", "xengine_c32_full.txt", "k_xengine_c32_32st_256ch_1024t", 32 * 256 * 1024 * 8 + 256 * 528 * 8),
+                           ("xe_pk.ncu-rep", "xengine_packed_full.txt", "k_xengine_tma_packed_16st_2pol_1024ch_1024t", 16 * 2 * 1024 * 1024 + 1024 * 136 * 4 * 8)):
+    b = summary(rep, R + "_" + dst)
     if b:
-        d[key] = {"bytes": int(b), "algorithmic_bytes": alg, "capture": "profiles/" + dst}
+        d[key] = {"bytes": int(b), "algorithmic_bytes": alg, "capture": "profiles/" + R + "_" + dst}
 json.dump(d, open(tj, "w"), indent=2)
-sass_hist("fft.ncu-rep", "r1_fft8192_sass_hist.txt", 8192)
-sass_hist("xe_tma.ncu-rep", "r1_xengine_sass_hist.txt", 1)
-print(open(os.path.join(PRO, "r1_launches_summary.txt")).read())
+sass_hist("fft.ncu-rep", R + "_fft8192_sass_hist.txt", 8192)
+sass_hist("xe_batch.ncu-rep", R + "_xengine_batch16_sass_hist.txt", 16)
+sass_hist("fftfilt.ncu-rep", R + "_fftfilt_sass_hist.txt", 1)
+print(open(os.path.join(PRO, R + "_launches_summary.txt")).read())

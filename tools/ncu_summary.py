@@ -43,9 +43,14 @@ def main():
                 except ValueError:
                     pass
         print("  top stalls (warps per issue): " + ", ".join("%s %.2f" % (n, v) for v, n in sorted(st, reverse=True)[:6]))
-        rd = float(vals[hdr.index("dram__bytes_read.sum")]) if "dram__bytes_read.sum" in hdr else 0
-        wr = float(vals[hdr.index("dram__bytes_write.sum")]) if "dram__bytes_write.sum" in hdr else 0
-        print("  dram traffic (read+write): %.3f %s" % (rd + wr, units[hdr.index("dram__bytes_read.sum")]))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+        def in_bytes(key):                      # read and write may be reported in different units
+            if key not in hdr:
+                return 0.0
+            i = hdr.index(key)
+            return float(vals[i].replace(",", "")) * scale.get(units[i], 1.0)
+        print("  dram traffic (read+write): %.3f Mbyte" % ((in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum")) / 1e6))
 
 
 if __name__ == "__main__":

@@ -54,6 +54,13 @@ elif what == "xengine_batch":
     blk = blocks.clXEngine(*gpu, False, capi.DTYPE_BYTE, 1, A, 1, 0, F, T, [])
     for i in range(reps):
         blk.launch_device_batch(buf.data_ptr(), vis.data_ptr(), K, sp)
+elif what == "xengine_packed":
+    A, F, T, npol = 16, 1024, 1024, 2
+    bufs = [torch.randint(0, 256, (T * A * F * npol,), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    vis = torch.empty(F * (A * (A + 1) // 2) * 4 * 2, dtype=torch.float32, device="cuda")
+    blk = blocks.clXEngine(*gpu, False, capi.DTYPE_PACKEDXY, npol, A, 1, 0, F, T, [])
+    for i in range(reps):
+        blk.launch_device(bufs[i % 3].data_ptr(), vis.data_ptr(), False, sp)
 elif what == "xengine_c32":
     A, F, T = 32, 256, 1024
     xc = torch.empty(T * A * F * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)

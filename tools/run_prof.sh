@@ -1,9 +1,13 @@
-# round-1 profile evidence: launch list of the bench command + one full capture per headline kernel
+# round-2 profile evidence: launch list of the bench command + one full capture per kernel (ncu replays each kernel
+# ~40 times: one GPU, never under torchrun)
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
-REPS=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_xengine_tma -s 1 -c 1 -f -o gpurun_out/xe_tma python tools/prof_one.py xengine > gpurun_out/ncu_xe.log 2>&1; echo "xe rc=$?"
-if [ -n "$PROF_ALL" ]; then
-REPS=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fft -s 1 -c 1 -f -o gpurun_out/fft python tools/prof_one.py fft > gpurun_out/ncu_fft.log 2>&1; echo "fft rc=$?"
-REPS=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fftfilt -s 1 -c 1 -f -o gpurun_out/fftfilt python tools/prof_one.py filter > gpurun_out/ncu_filt.log 2>&1; echo "filt rc=$?"
-REPS=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pfb -s 1 -c 1 -f -o gpurun_out/pfb python tools/prof_one.py pfb > gpurun_out/ncu_pfb.log 2>&1; echo "pfb rc=$?"
-fi
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
+cap() { REPS=3 timeout 300 ncu --set full --clock-control none --import-source on -k regex:$1 -s 1 -c 1 -f -o gpurun_out/$2 python tools/prof_one.py $3 > gpurun_out/ncu_$2.log 2>&1; echo "$2 rc=$?"; }
+cap k_xengine_tma xe_tma xengine
+cap k_xengine_tma xe_batch xengine_batch
+cap k_xengine_tma xe_pk xengine_packed
+cap k_xengine_c32 xe_c32 xengine_c32
+cap "k_fft<" fft fft
+cap k_fftfilt fftfilt filter
+cap k_fir fir fir
+cap k_pfb pfb pfb
