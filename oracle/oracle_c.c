@@ -17,12 +17,12 @@
  *     counters are the reference's code; the innermost library kernels (FFT
  *     butterflies, dot products) are the shim's;
  *   - numeric ids: include/clenabled/*.h + grc/*.yml (ref_constants.json).
- * Still "parity unpinned" by reference outputs (every *_impl.cc needs GNU Radio,
- * OpenCL and clFFT, and its arithmetic lives in OpenCL C strings): the FFT
- * butterflies themselves, the polyphase channelizer and the X-engine; they rest
- * on the reference tools' known-answer inputs (const (1.0,0.5)*2, the sin/cos
- * tone, ramp taps) and on independent implementations of the published maths
- * (pocketfft, scipy.signal, exact int64 einsum) -- tests/test_oracle.py.
+ *   - the device arithmetic itself: the OpenCL kernel strings XCorrelate, CharToComplex (IChar and packed-XY LUT),
+ *     filterpfb2 + channel_map and opconst_complex, emitted by the reference's OWN builder functions (their bodies
+ *     are compiled from where they lie into a generator) and run on the CPU against oracle/shim/opencl_c.h
+ *     (oracle/ref_kernels.py, ref_kernels.npz).
+ * Not runnable here: clFFT (third-party library: the DFT it is planned for is taken from its published definition and
+ * checked against pocketfft) and the reference's host classes around the kernels (GNU Radio, OpenCL C++ API).
  *
  * Every function cites the reference file:line it follows
  * (paths relative to the reference tree).

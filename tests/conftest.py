@@ -38,7 +38,7 @@ def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
     out = {}
-    for f in ("ref_firdes_window.npz", "kat.npz", "ref_filters.npz"):
+    for f in ("ref_firdes_window.npz", "kat.npz", "ref_filters.npz", "ref_kernels.npz"):
         with np.load(os.path.join(d, f)) as z:
             out.update({k: z[k] for k in z.files})
     return out

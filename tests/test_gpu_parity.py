@@ -478,6 +478,33 @@ def test_xengine_packed_4bit_fused_unpack_bit_exact(A, F, T, npol, monkeypatch):
     assert rel_err(vis, (want[:, 0] + 1j * want[:, 1]) / 49.0) < 1e-6
 
 
+def test_xengine_and_channelizer_match_reference_kernel_outputs(golden):
+    """the CUDA path against outputs of the reference's OWN OpenCL kernels (tests/golden/ref_kernels.npz: XCorrelate,
+    CharToComplex incl. the packed-XY LUT, filterpfb2 + channel_map; source text emitted by the reference's builder
+    functions and run on the CPU by oracle/ref_kernels.py)"""
+    for A, F, T, npol, seed in [(5, 4, 33, 2, 6101), (3, 6, 16, 1, 6102), (32, 2, 64, 1, 6103), (16, 3, 40, 2, 6104)]:
+        x = orc.rng_c32(T * A * F * npol, seed)
+        got = _xe(capi.DTYPE_COMPLEX, npol, A, F, T).work(x)
+        assert rel_err(got, golden["xc_c32_%d_%d_%d_%d_fma1" % (A, F, T, npol)]) < TOL
+    for A, F, T, npol, seed in [(4, 8, 64, 1, 6201), (3, 4, 32, 2, 6202), (32, 4, 128, 1, 6203)]:
+        b = orc.rng_i8(T * A * F * npol * 2, seed)
+        assert rel_err(_xe(capi.DTYPE_BYTE, npol, A, F, T).work(b), golden["xc_i8_%d_%d_%d_%d" % (A, F, T, npol)]) < TOL
+    for A, F, T, seed in [(4, 16, 32, 6301), (16, 16, 64, 6302)]:
+        p = orc.rng_i8(T * A * F * 2, seed).view(np.uint8)
+        assert rel_err(_xe(capi.DTYPE_PACKEDXY, 2, A, F, T).work(p), golden["xc_packed_%d_%d_%d" % (A, F, T)]) < TOL
+    for M, R, ntaps, niter, cmap, seed in [(8, 8, 24, 19, None, 6401), (8, 4, 19, 21, None, 6402), (64, 64, 128, 16, None, 6403),
+                                           (16, 16, 40, 9, [5, 0, 15, 3], 6404)]:
+        taps = (orc.rng_f32(ntaps, seed) * 0.1).astype(np.float32)
+        x = orc.rng_c32((niter - 1) * R + ntaps + (M - R), seed + 50)
+        cm = list(range(M)) if cmap is None else cmap
+        blk = blocks.clPolyphaseChannelizer(*GPU, taps, M * 4, M, R, cm)
+        want = golden["pfb_%d_%d_%d_%d_%d" % (M, R, ntaps, niter, 0 if cmap is None else len(cmap))]
+        assert rel_err(blk.work(x, niter), want) < TOL
+    xm = orc.rng_c32(256, orc.SEED_M)
+    for op in (1, 2, 3, 4):
+        assert np.array_equal(blocks.clMathConst(capi.DTYPE_COMPLEX, *GPU, 0.7071, op).work(xm), golden["mathconst_op%d" % op])
+
+
 def test_xengine_channel_shard_matches_full():
     A, F, T = 8, 64, 128
     buf = orc.rng_i8(T * A * F * 2, orc.SEED_X + 5)

@@ -269,6 +269,66 @@ def test_filter_fixture_is_what_the_live_reference_build_gives(golden):
         assert np.array_equal(np.concatenate(ys), golden[name + "_fft"])
 
 
+# ---- 1b. reference code: the OpenCL kernels themselves ------------------------------
+# tests/golden/ref_kernels.npz holds outputs of the reference's OWN kernels -- XCorrelate, CharToComplex (IChar and
+# packed-XY LUT), filterpfb2 + channel_map, opconst_complex -- whose source text is emitted by the reference's builder
+# functions and run on the CPU (oracle/ref_kernels.py, tests/golden/make_ref_kernels.py).
+XC_COMPLEX = [(5, 4, 33, 2, 6101), (3, 6, 16, 1, 6102), (32, 2, 64, 1, 6103), (16, 3, 40, 2, 6104)]
+XC_ICHAR = [(4, 8, 64, 1, 6201), (3, 4, 32, 2, 6202), (32, 4, 128, 1, 6203)]
+XC_PACKED = [(4, 16, 32, 6301), (16, 16, 64, 6302)]
+PFB_CASES = [(8, 8, 24, 19, None, 6401), (8, 4, 19, 21, None, 6402), (64, 64, 128, 16, None, 6403), (16, 16, 40, 9, [5, 0, 15, 3], 6404)]
+
+
+def test_oracle_xengine_matches_reference_kernel_outputs(golden):
+    for A, F, T, npol, seed in XC_COMPLEX:
+        x = orc.rng_c32(T * A * F * npol, seed)
+        got = orc.xengine_f32(x, A, F, T, npol)
+        for fma in (0, 1):                                   # the reference builds either form, by device capability
+            assert rel_err(got, golden["xc_c32_%d_%d_%d_%d_fma%d" % (A, F, T, npol, fma)]) < 1e-6
+    for A, F, T, npol, seed in XC_ICHAR:
+        b = orc.rng_i8(T * A * F * npol * 2, seed)
+        want = golden["xc_i8_%d_%d_%d_%d" % (A, F, T, npol)]
+        assert rel_err(orc.xengine_f32(b, A, F, T, npol), want) < 1e-6
+        ex = orc.xengine_exact(b, A, F, T, npol).astype(np.float64) / (127.0 * 127.0)
+        assert rel_err(ex[:, 0] + 1j * ex[:, 1], want) < 1e-5     # the exact integers, scaled like CharToComplex does
+    lut = orc.unpack4(np.arange(256, dtype=np.uint8)).astype(np.float32).reshape(-1, 2)
+    assert rel_err(lut[:, 0] + 1j * lut[:, 1], golden["packed_lut_all_bytes"] * 7.0) < 1e-6      # every byte through the LUT
+    for A, F, T, seed in XC_PACKED:
+        p = orc.rng_i8(T * A * F * 2, seed).view(np.uint8)
+        ex = orc.xengine_exact(orc.unpack4(p), A, F, T, 2).astype(np.float64) / 49.0
+        assert rel_err(ex[:, 0] + 1j * ex[:, 1], golden["xc_packed_%d_%d_%d" % (A, F, T)]) < 1e-5
+
+
+def test_oracle_channelizer_and_mathconst_match_reference_kernel_outputs(golden):
+    for M, R, ntaps, niter, cmap, seed in PFB_CASES:
+        taps = (orc.rng_f32(ntaps, seed) * 0.1).astype(np.float32)
+        x = orc.rng_c32((niter - 1) * R + ntaps + (M - R), seed + 50)
+        cm = list(range(M)) if cmap is None else cmap
+        want = golden["pfb_%d_%d_%d_%d_%d" % (M, R, ntaps, niter, 0 if cmap is None else len(cmap))]
+        assert rel_err(orc.pfb(x, taps, M, R, cm, niter), want) < 1e-5
+    xm = orc.rng_c32(256, orc.SEED_M)
+    for op in (1, 2, 3, 4):
+        assert np.array_equal(orc.mathconst(xm, 0.7071, op), golden["mathconst_op%d" % op])
+    # MATHOP_EMPTY_W_COPY: the reference's OpenCL string falls through into the multiply (missing break,
+    # lib/clMathConst_impl.cc:187-193) while its CPU path copies; this repo copies (deviations)
+    assert np.array_equal(golden["mathconst_op254"], golden["mathconst_op1"])
+    assert np.array_equal(orc.mathconst(xm, 0.7071, 254), xm)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_kernels", fromlist=["x"]).available(), reason="reference tree absent")
+def test_reference_kernel_fixture_is_what_the_reference_sources_emit_now(golden):
+    from oracle import ref_kernels as rk
+    A, F, T, npol, seed = XC_COMPLEX[0]
+    x = orc.rng_c32(T * A * F * npol, seed)
+    assert np.array_equal(rk.xcorrelate(x, A, F, T, npol, True), golden["xc_c32_%d_%d_%d_%d_fma1" % (A, F, T, npol)])
+    M, R, ntaps, niter, cmap, seed = PFB_CASES[1]
+    taps = (orc.rng_f32(ntaps, seed) * 0.1).astype(np.float32)
+    xp = orc.rng_c32((niter - 1) * R + ntaps + (M - R), seed + 50)
+    assert np.array_equal(rk.pfb(xp, taps, M, R, list(range(M)), niter), golden["pfb_%d_%d_%d_%d_0" % (M, R, ntaps, niter)])
+    src = rk.kernel_source("xcorr", 3, 4, 8, 2, 1, 0, 1)
+    assert "__kernel void XCorrelate" in src and "#define d_num_baselines 6" in src
+
+
 @pytest.mark.parametrize("M,R,T", [(8, 8, 24), (8, 4, 19), (64, 64, 128)])
 def test_pfb_vs_direct_definition(M, R, T):
     taps = (orc.rng_f32(T, orc.SEED_P) * 0.1).astype(np.float32)
