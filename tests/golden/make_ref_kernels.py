@@ -49,6 +49,14 @@ def main():
     xm = orc.rng_c32(256, orc.SEED_M)
     for op in (1, 2, 3, 4, 254):
         out["mathconst_op%d" % op] = rk.mathconst(xm, 0.7071, op)
+    a, b = orc.rng_c32(256, 6501), orc.rng_c32(256, 6502)
+    for op in (1, 2, 3, 5):
+        out["mathop_op%d" % op] = rk.mathop(a, b, op)
+    for K, seed in ((37, 6601), (256, 6602)):
+        taps = (orc.rng_f32(K, seed) / K).astype(np.float32)
+        x = orc.rng_c32(600 + K - 1, seed + 50)               # K-1 history samples + 600 new ones
+        for fma in (0, 1):
+            out["tdfir_%d_fma%d" % (K, fma)] = rk.td_fir(x, taps, bool(fma))
     np.savez_compressed(os.path.join(HERE, "ref_kernels.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -503,6 +503,16 @@ def test_xengine_and_channelizer_match_reference_kernel_outputs(golden):
     xm = orc.rng_c32(256, orc.SEED_M)
     for op in (1, 2, 3, 4):
         assert np.array_equal(blocks.clMathConst(capi.DTYPE_COMPLEX, *GPU, 0.7071, op).work(xm), golden["mathconst_op%d" % op])
+    a, b = orc.rng_c32(256, 6501), orc.rng_c32(256, 6502)
+    for op in (1, 2, 3, 5):
+        assert np.array_equal(blocks.clMathOp(capi.DTYPE_COMPLEX, *GPU, op).work(a, b), golden["mathop_op%d" % op])
+    for K, seed in ((37, 6601), (256, 6602)):                 # td_FIR_complex: history = the first K-1 samples
+        taps = (orc.rng_f32(K, seed) / K).astype(np.float32)
+        x = orc.rng_c32(600 + K - 1, seed + 50)
+        for use_time in (True, False):
+            blk = blocks.clFilter(*GPU, 1, taps, 1, 0, use_time)
+            y = blk.work(x)                                   # zero initial state: the first K-1 outputs are the warm-up
+            assert rel_err(y[K - 1:], golden["tdfir_%d_fma1" % K]) < TOL
 
 
 def test_xengine_channel_shard_matches_full():

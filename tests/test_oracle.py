@@ -309,6 +309,14 @@ def test_oracle_channelizer_and_mathconst_match_reference_kernel_outputs(golden)
     xm = orc.rng_c32(256, orc.SEED_M)
     for op in (1, 2, 3, 4):
         assert np.array_equal(orc.mathconst(xm, 0.7071, op), golden["mathconst_op%d" % op])
+    a, b = orc.rng_c32(256, 6501), orc.rng_c32(256, 6502)
+    for op in (1, 2, 3, 5):                                   # two-input op_complex (lib/clMathOp_impl.cc:178-236)
+        assert np.array_equal(orc.mathop(a, b, op), golden["mathop_op%d" % op])
+    for K, seed in ((37, 6601), (256, 6602)):                 # td_FIR_complex (lib/clFilter_impl.cc:162-194)
+        taps = (orc.rng_f32(K, seed) / K).astype(np.float32)
+        x = orc.rng_c32(600 + K - 1, seed + 50)
+        assert np.array_equal(orc.fir(x, taps, 1), golden["tdfir_%d_fma0" % K])
+        assert rel_err(orc.fir(x, taps, 1), golden["tdfir_%d_fma1" % K]) < 1e-6
     # MATHOP_EMPTY_W_COPY: the reference's OpenCL string falls through into the multiply (missing break,
     # lib/clMathConst_impl.cc:187-193) while its CPU path copies; this repo copies (deviations)
     assert np.array_equal(golden["mathconst_op254"], golden["mathconst_op1"])
