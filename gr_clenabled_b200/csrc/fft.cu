@@ -337,17 +337,123 @@ struct Fft : clb200_block {
     int resident = 1;     // CTAs per SM the launch is sized for
     bool use_pf = false;  // bulk-copy prefetching kernel available and enabled
     bool use_tw1s = false; // pass-1 twiddles in shared memory (k_fft<.., MODE|4>)
+    // sizes above 16384 (one CTA's shared memory): N = n1 x n2, two passes of the in-SM kernels around transposes
+    bool big = false;
+    int n1 = 0, n2 = 0;
+    clb200_handle sub1 = nullptr, sub2 = nullptr;      // n1- and n2-point plans (complex, no window, no shift)
+    struct Scratch {
+        cudaStream_t st = nullptr;
+        Buf a, b;
+    } scratch[4];                                      // per launching stream (the host path rotates over 3)
     ~Fft() override
     {
         DeviceGuard g(device);
         d_tw.release();
         d_win.release();
+        for (auto &sc : scratch) {
+            sc.a.release();
+            sc.b.release();
+        }
+        if (sub1) clb200_destroy(sub1);
+        if (sub2) clb200_destroy(sub2);
     }
 };
+
+// ---- sizes above 16384: four-step decomposition --------------------------------------------------------------
+// x[n], n = n2 + N2*n1   ->   X[k1 + N1*k2] = sum_n2 [ W_N^(n2 k1) ( sum_n1 x[N2 n1 + n2] W_N1^(n1 k1) ) ] W_N2^(n2 k2)
+// as: transpose-in (window, backward half swap, real -> complex)  ->  N1-point FFTs over contiguous vectors
+//     ->  twiddle + transpose  ->  N2-point FFTs  ->  transpose-out (forward half swap).
+// Every FFT pass is the in-SM kernel at its HBM rate; the three transposes are what the size costs.
+// out[v][c][r] = f(in[v][r][c]), 32 x 32 tiles through shared memory, both sides coalesced
+template <int MODE>      // 0: in, 1: twiddle, 2: out
+__global__ void __launch_bounds__(256) k_fft_tr(const void *__restrict__ in, float2 *__restrict__ out, int rows, int cols,
+                                                long nvec, const float *__restrict__ win, int n, int xor_idx, float sign,
+                                                int real_in)
+{
+    __shared__ float2 tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (long v = blockIdx.z; v < nvec; v += gridDim.z) {
+        const long base = v * (long)n;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int r = r0 + ty + 8 * k, c = c0 + tx;
+            float2 val = make_float2(0.f, 0.f);
+            if (r < rows && c < cols) {
+                const int idx = r * cols + c;
+                if (MODE == 0) {
+                    const int src = idx ^ xor_idx;                       // backward + shift: input halves swapped
+                    val = real_in ? make_float2(reinterpret_cast<const float *>(in)[base + src], 0.f)
+                                  : reinterpret_cast<const float2 *>(in)[base + src];
+                    if (win != nullptr) {                                // the window multiplies the (swapped) buffer
+                        const float w = win[idx];
+                        val.x *= w;
+                        val.y *= w;
+                    }
+                } else {
+                    val = reinterpret_cast<const float2 *>(in)[base + idx];
+                    if (MODE == 1) {                                     // W_N^(n2 k1): row = n2, column = k1
+                        const unsigned ph = ((unsigned)r * (unsigned)c) & (unsigned)(n - 1);
+                        float sn, cs;
+                        sincospif(2.0f * (float)ph / (float)n, &sn, &cs);
+                        sn *= sign;
+                        val = make_float2(val.x * cs - val.y * sn, val.x * sn + val.y * cs);
+                    }
+                }
+            }
+            tile[ty + 8 * k][tx] = val;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = c0 + ty + 8 * k, r = r0 + tx;                  // transposed: consecutive lanes -> consecutive r
+            if (r < rows && c < cols) {
+                int o = c * rows + r;
+                if (MODE == 2) o ^= xor_idx;                             // forward + shift: output halves swapped
+                out[base + o] = tile[tx][ty + 8 * k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st);
+
+int fft_launch_big(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
+{
+    Fft::Scratch *sc = nullptr;
+    for (auto &c : f->scratch)
+        if (c.st == st && c.a.p) sc = &c;
+    if (!sc)
+        for (auto &c : f->scratch)
+            if (!c.a.p && !sc) sc = &c;
+    if (!sc) sc = &f->scratch[0];
+    sc->st = st;
+    const size_t bytes = (size_t)nvec * f->n * sizeof(float2);
+    CLB_TRY(sc->a.reserve(bytes));
+    CLB_TRY(sc->b.reserve(bytes));
+    float2 *ta = (float2 *)sc->a.p, *tb = (float2 *)sc->b.p;
+    const int N1 = f->n1, N2 = f->n2, half = f->n >> 1;
+    const int gz = (int)std::min<long>(nvec, 64);
+    const float sign = f->dir < 0 ? -1.f : 1.f;
+    // x as [n1][n2] -> [n2][n1]
+    k_fft_tr<0><<<dim3((N2 + 31) / 32, (N1 + 31) / 32, gz), 256, 0, st>>>(
+        d_in, ta, N1, N2, nvec, f->has_window ? (const float *)f->d_win.p : nullptr, f->n,
+        (f->shift && f->dir > 0) ? half : 0, sign, f->dtype == CLB200_DTYPE_FLOAT);
+    CLB_TRY(fft_launch(static_cast<Fft *>(f->sub1), ta, tb, nvec * N2, st));            // over n1 -> [n2][k1]
+    k_fft_tr<1><<<dim3((N1 + 31) / 32, (N2 + 31) / 32, gz), 256, 0, st>>>(tb, ta, N2, N1, nvec, nullptr, f->n, 0, sign, 0);
+    CLB_TRY(fft_launch(static_cast<Fft *>(f->sub2), ta, tb, nvec * N1, st));            // over n2 -> [k1][k2]
+    k_fft_tr<2><<<dim3((N2 + 31) / 32, (N1 + 31) / 32, gz), 256, 0, st>>>(tb, (float2 *)d_out, N1, N2, nvec, nullptr, f->n,
+                                                                          (f->shift && f->dir < 0) ? half : 0, sign, 0);
+    CLB_CUDA(cudaGetLastError());
+    f->n_launch += 3;
+    return CLB200_OK;
+}
 
 int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
 {
     if (nvec <= 0) return CLB200_OK;
+    if (f->big) return fft_launch_big(f, d_in, d_out, nvec, st);
     const FftVariant *v = f->var;
     long ntile = (nvec + v->batch - 1) / v->batch;
     int grid = grid_for(ntile, device_sm_count(f->device), f->resident);
@@ -521,8 +627,8 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
                       int device, int shift, clb200_handle *out)
 {
     CLB_CHECK(out != nullptr, CLB200_EINVAL, "null out");
-    CLB_CHECK(fft_size >= 2 && (fft_size & (fft_size - 1)) == 0 && fft_size <= 16384, CLB200_EINVAL,
-              "clFFT: fft size %d is not a power of two in 2..16384", fft_size);
+    CLB_CHECK(fft_size >= 2 && (fft_size & (fft_size - 1)) == 0 && fft_size <= (1 << 22), CLB200_EINVAL,
+              "clFFT: fft size %d is not a power of two in 2..4194304", fft_size);
     CLB_CHECK(dir == CLB200_FFT_FORWARD || dir == CLB200_FFT_BACKWARD, CLB200_EINVAL,
               "clFFT: direction must be -1 (forward) or 1 (backward), got %d", dir);
     // lib/clFFT_impl.cc:74-76: "window not the same length as fft_size"
@@ -548,11 +654,33 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
     // the reference shifts complex data only: a real-input spectrum is left unshifted (lib/clFFT_impl.cc:594)
     f->shift = (shift && dtype == CLB200_DTYPE_COMPLEX) ? 1 : 0;
     f->mode = dtype == CLB200_DTYPE_FLOAT ? 2 : (dir > 0 ? 1 : 0);
-    f->var = pick_variant(f->logn);
     auto fail = [&](int rc) {
         delete f;
         return rc;
     };
+    if (fft_size > 16384) {
+        // four-step path: two plans of the in-SM kernels (n1 >= n2, both <= 16384 up to 2^28) + transposes
+        f->big = true;
+        f->n1 = 1 << ((f->logn + 1) / 2);
+        f->n2 = fft_size / f->n1;
+        if (window_len) {
+            f->has_window = true;
+            if (f->d_win.reserve(sizeof(float) * fft_size) != CLB200_OK) return fail(CLB200_ENOMEM);
+            if (cudaMemcpy(f->d_win.p, window, sizeof(float) * fft_size, cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("clFFT: window upload failed");
+                return fail(CLB200_ECUDA);
+            }
+        }
+        int rc = clb200_fft_create(f->n1, dir, nullptr, 0, CLB200_DTYPE_COMPLEX, device, 0, &f->sub1);
+        if (rc == CLB200_OK) rc = clb200_fft_create(f->n2, dir, nullptr, 0, CLB200_DTYPE_COMPLEX, device, 0, &f->sub2);
+        if (rc != CLB200_OK) return fail(rc);
+        f->set_info("clFFT %d-pt %s: four-step, %d x %d-pt and %d x %d-pt in-SM passes around three tiled transposes "
+                    "(window / half swaps / twiddles fused into the transposes)", fft_size, dir < 0 ? "forward" : "backward",
+                    f->n2, f->n1, f->n1, f->n2);
+        *out = f;
+        return CLB200_OK;
+    }
+    f->var = pick_variant(f->logn);
     if (!f->var) {
         set_error("clFFT: no kernel for size %d", fft_size);
         return fail(CLB200_EINVAL);

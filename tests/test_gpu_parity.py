@@ -167,6 +167,29 @@ def test_fft_real_input_and_streams():
         assert rel_err(oi, orc.fft(xi, N, -1)) < TOL
 
 
+@pytest.mark.parametrize("N", [32768, 65536, 1 << 18, 1 << 20])
+def test_fft_sizes_above_16384_four_step(N):
+    """sizes beyond one CTA's shared memory (clFFT plans accept them: waterfalls of 32768 / 65536 points): four-step
+    decomposition, every window / shift / direction / real-input combination against the oracle and pocketfft"""
+    nvec = 3 if N <= 65536 else 1
+    x = orc.rng_c32(N * nvec, orc.SEED_F + 20)
+    w = orc.window_blackman(N)
+    ref = np.fft.fft(x.astype(np.complex128).reshape(nvec, N), axis=1).reshape(-1)
+    got = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU).work(x)
+    assert rel_err(got, ref) < 2e-6
+    assert rel_err(got, orc.fft(x, N, -1)) < TOL
+    if N <= 65536:
+        for direction in (capi.FFT_FORWARD, capi.FFT_BACKWARD):
+            for win in (None, w):
+                for shift in (False, True):
+                    blk = blocks.clFFT(N, direction, [] if win is None else win, capi.DTYPE_COMPLEX, *GPU, 0, 1, shift)
+                    assert rel_err(blk.work(x), orc.fft(x, N, direction, win, shift)) < TOL, (direction, win is None, shift)
+        xr = orc.rng_f32(N * nvec, orc.SEED_F + 21)
+        assert rel_err(blocks.clFFT(N, capi.FFT_FORWARD, w, capi.DTYPE_FLOAT, *GPU, 0, 1, True).work(xr), orc.fft_real(xr, N, w)) < TOL
+    back = blocks.clFFT(N, capi.FFT_BACKWARD, [], capi.DTYPE_COMPLEX, *GPU).work(got) / N
+    assert rel_err(back, x) < TOL
+
+
 @pytest.mark.parametrize("N", [2, 8, 64, 1024, 8192, 16384])
 def test_fft_real_input_sizes_window_and_ignored_shift(N, golden):
     """dtype FLOAT: full Hermitian spectrum, window applied, and the shift flag ignored like the reference
