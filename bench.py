@@ -199,17 +199,22 @@ def run_reference(args, rank):
         return
     import numpy as np
     from oracle import oracle as orc
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:                        # noqa: BLE001
+        cores = os.cpu_count() or 1
     nvec = args.nvec
     x = orc.rng_c32(FFT_N * nvec, orc.SEED_F).reshape(nvec, FFT_N)
-    # pick the faster implementation on a short trial, then time exactly `steps` steps of it
+    # pick the fastest (implementation, thread count) on a short trial, then time exactly `steps` steps of it
     trial = {}
     for impl in ("pocketfft", "oracle_radix2"):
-        try:
-            trial[impl] = cpu_fft_rate(impl, min(nvec, 1024), cores, 0.5, x[:min(nvec, 1024)])[0]
-        except Exception:                    # noqa: BLE001
-            trial[impl] = 0.0
-    impl = max(trial, key=trial.get)
+        for th in sorted({cores, max(1, cores // 2)}, reverse=True):
+            try:
+                trial["%s_%dthreads" % (impl, th)] = cpu_fft_rate(impl, min(nvec, 1024), th, 0.5, x[:min(nvec, 1024)])[0]
+            except Exception:                # noqa: BLE001
+                trial["%s_%dthreads" % (impl, th)] = 0.0
+    best = max(trial, key=trial.get)
+    impl, cores = best.rsplit("_", 1)[0], int(best.rsplit("_", 1)[1].replace("threads", ""))
     orc.lib().orc_set_threads(cores)
     for _ in range(max(1, min(args.warmup, 3))):
         _cpu_fft_step(impl, x, cores)
@@ -313,14 +318,17 @@ def secondary_blocks(torch, blocks, capi, dev, stream_ptr, hbm_peak):
                                                   "unit": "TFLOP/s", "frac": fl / fp["ffma_tflops"],
                                                   "flop_per_sample": 1024}
                 else:
-                    # two 1024-point FFTs (5 N log2 N flop each) + 1024 complex multiplies per 769 new samples;
-                    # butterflies are additions and multiplications (one flop per lane-op), so the lane rate
-                    # (= the measured FADD rate, half the FFMA flop rate) is the denominator
-                    fps = (2 * 5 * 1024 * 10 + 6 * 1024) / 769.0
-                    fl = fps * n / t / 1e12
-                    out[name]["roofline_fp32"] = {"bound": "fp32 lanes (non-fused adds / multiplies)", "achieved": fl,
-                                                  "peak": fp["fadd_tflops"], "unit": "TFLOP/s (1 flop per lane-op)",
-                                                  "frac": fl / fp["fadd_tflops"], "flop_per_sample": fps}
+                    # executed FP32 lane operations per sample, counted from the SASS histogram of the ncu capture of
+                    # this launch shape (profiles/r2_fftfilt_sass_hist.txt: 2 x FADD2 + FMUL + FFMA + FADD warp
+                    # instructions x 32 lanes / 64 Mi samples); the nominal count (two 1024-point FFTs at 5 N log2 N
+                    # + 1024 complex multiplies per 769 new samples) is given beside it
+                    lane_ops = (2 * 55851520 + 40143280 + 30369264 + 9774016) * 32.0 / (1 << 26)
+                    tl = lane_ops * n / t / 1e12
+                    out[name]["roofline_fp32"] = {"bound": "fp32 lanes (one add, multiply or fma per lane and clock)",
+                                                  "achieved": tl, "peak": fp["fadd2_tflops"], "unit": "T lane-ops/s",
+                                                  "frac": tl / fp["fadd2_tflops"], "lane_ops_per_sample": lane_ops,
+                                                  "lane_ops_source": "profiles/r2_fftfilt_sass_hist.txt",
+                                                  "nominal_flop_per_sample": (2 * 5 * 1024 * 10 + 6 * 1024) / 769.0}
     except Exception as e:                           # noqa: BLE001
         out["clFilter"] = {"error": str(e)}
     try:
@@ -713,6 +721,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host threads (measured:
+        # pocketfft drops from 430 to 100 Msamples/s on 8 cores with it set), so it is dropped before numpy / scipy /
+        # the OpenMP runtime of the oracle are loaded
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ.pop(k, None)
         run_reference(args, rank)
         return
 
