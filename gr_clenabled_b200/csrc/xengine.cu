@@ -71,6 +71,7 @@ struct XeParams {
     unsigned *gather_flag[8];       // per destination rank: address of ITS flag word for this source rank (or null)
     unsigned *gather_flag_mc;       // multicast address of the flag word for this source rank (or null)
     unsigned *gather_counter;       // CTAs of this launch that have finished their stores
+    int gather_fence_gpu;
     unsigned gather_epoch;
 };
 
@@ -992,6 +993,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.gather_mc = nullptr;
     p.gather_flag_mc = nullptr;
     p.gather_counter = nullptr;
+    p.gather_fence_gpu = 0;
     p.gather_epoch = 0;
     for (int r = 0; r < 8; r++) p.gather_flag[r] = nullptr;
     if (gather && x->gather_rank >= 0) {
@@ -1000,7 +1002,8 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         // CLB200_XE_GATHER_INKERNEL=1: the kernel's last CTA releases the flags itself (every CTA then waits for the
         // acknowledgement of its peer stores before it leaves its SM: measured 27.8 vs ... us per launch at 2 GPUs);
         // default: the flags are released by the one-warp kernel that clb200_xengine_gather_wait enqueues behind it
-        static const bool inkernel = [] { const char *e = getenv("CLB200_XE_GATHER_INKERNEL"); return e && atoi(e); }();
+        static const int inkernel = [] { const char *e = getenv("CLB200_XE_GATHER_INKERNEL"); return e ? atoi(e) : 0; }();
+        p.gather_fence_gpu = inkernel == 2;      // 2: CTAs release at GPU scope, only the last CTA fences system-wide
         if (inkernel) {
             p.gather_counter = (unsigned *)x->d_gather_counter.p;
             if (x->gather_flags_mc) p.gather_flag_mc = x->gather_flags_mc + (size_t)x->gather_rank * CLB200_XENGINE_FLAG_STRIDE;
@@ -1494,7 +1497,10 @@ int clb200_xengine_gather_wait(clb200_handle h, void *stream)
     gs.local = x->gather_flags[x->gather_rank];
     gs.epoch = x->gather_epoch;
     gs.nranks = x->ngather;
-    gs.signal = 1;
+    {
+        const char *e = getenv("CLB200_XE_GATHER_INKERNEL");
+        gs.signal = !(e && atoi(e));             // the kernel's last CTA has released the flags already
+    }
     gs.wait = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);

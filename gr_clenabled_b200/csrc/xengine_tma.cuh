@@ -621,7 +621,8 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
         // readers.  (A fence by all 512 threads instead of one cost 15 us per launch.) ----
         tm_worker_sync();
         if (threadIdx.x == 0) {
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            if (p.gather_fence_gpu) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            else asm volatile("fence.acq_rel.sys;" ::: "memory");
             const unsigned old = atomicAdd(p.gather_counter, 1u);
             if (old == gridDim.x - 1) {
                 atomicExch(p.gather_counter, 0u);                      // ready for the next launch
