@@ -101,6 +101,46 @@ def test_secondary_elementwise():
     assert np.allclose(blocks.clMagPhaseToComplex(*GPU).work(m, p), x, rtol=1e-4, atol=1e-6)
 
 
+def test_empty_calls_and_bad_arguments_for_every_block():
+    """zero items is a valid call for every block (the scheduler may offer none); constructor checks throw like the
+    reference's (clFFT window length :74-76, channelizer buf_items :59-62, X-engine inputs :106-109)"""
+    e = np.zeros(0, c64)
+    ef = np.zeros(0, np.float32)
+    assert blocks.clMathConst(capi.DTYPE_COMPLEX, *GPU, 2.0, capi.OP_MULTIPLY).work(e).size == 0
+    assert blocks.clMathOp(capi.DTYPE_COMPLEX, *GPU, capi.OP_ADD).work(e, e).size == 0
+    assert blocks.clLog(*GPU, 10.0, 0.0).work(ef).size == 0
+    assert blocks.clComplexToMag(*GPU).work(e).size == 0
+    assert blocks.clFFT(1024, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU).work(e).size == 0
+    assert blocks.clFFT(65536, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU).work(e).size == 0
+    taps = np.ones(16, np.float32) / 16
+    for use_time in (False, True):
+        f = blocks.clFilter(*GPU, 2, taps, 1, 0, use_time)
+        assert f.work(e).size == 0
+        assert f.work(np.ones(1, c64)).size == 1 and f.work(np.ones(1, c64)).size == 0     # decimation phase carried
+    assert blocks.clQuadratureDemod(1.0, *GPU).work(e).size == 0
+    for bad in (lambda: blocks.clFFT(1000, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU),            # not a power of two
+                lambda: blocks.clFFT(1024, capi.FFT_FORWARD, np.ones(100, np.float32), capi.DTYPE_COMPLEX, *GPU),
+                lambda: blocks.clFFT(1024, 0, [], capi.DTYPE_COMPLEX, *GPU),
+                lambda: blocks.clFFT(1024, capi.FFT_BACKWARD, [], capi.DTYPE_FLOAT, *GPU),             # real input is forward-only
+                lambda: blocks.clFFT(1 << 23, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU),
+                lambda: blocks.clFilter(*GPU, 0, taps),
+                lambda: blocks.clFilter(*GPU, 1, np.zeros(0, np.float32)),
+                lambda: blocks.clPolyphaseChannelizer(*GPU, taps, 100, 8, 8, list(range(8))),
+                lambda: blocks.clPolyphaseChannelizer(*GPU, taps, 64, 12, 12, list(range(12))),         # not a power of two
+                lambda: _xe(capi.DTYPE_BYTE, 1, 1, 8, 8),
+                lambda: _xe(capi.DTYPE_BYTE, 3, 4, 8, 8),
+                lambda: _xe(capi.DTYPE_SHORT, 1, 4, 8, 8),
+                lambda: _xe(capi.DTYPE_BYTE, 2, 33, 8, 8),                                            # > 64 rows
+                lambda: blocks.clMathConst(99, *GPU, 1.0, capi.OP_MULTIPLY)):
+        with pytest.raises(capi.Clb200Error) as ei:
+            bad()
+        assert ei.value.code == capi.EINVAL
+    xe = _xe(capi.DTYPE_BYTE, 1, 4, 8, 8)
+    with pytest.raises(capi.Clb200Error) as ei:                                                      # stream calls before stream_begin
+        xe.push([np.zeros(16, np.int8)] * 4, 1)
+    assert ei.value.code == capi.ESTATE
+
+
 # ------------------------------------------------------------------------- clFFT --
 @pytest.mark.parametrize("N", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
 def test_fft_forward_all_sizes(N):
