@@ -72,6 +72,7 @@ struct XeParams {
     unsigned *gather_flag_mc;       // multicast address of the flag word for this source rank (or null)
     unsigned *gather_counter;       // CTAs of this launch that have finished their stores
     int gather_fence_gpu;
+    int pdl_nowait;                 // consecutive launches are independent: no griddepcontrol.wait
     unsigned gather_epoch;
 };
 
@@ -994,6 +995,15 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.gather_flag_mc = nullptr;
     p.gather_counter = nullptr;
     p.gather_fence_gpu = 0;
+    {
+        // CLB200_XE_PDL_NOWAIT=1 (measurement only): consecutive launches skip griddepcontrol.wait, so their CTAs
+        // interleave as SMs free up (21.6 -> 18.7 us at 1024 channels, 12.2 -> 6.8 us at 128).  NOT the default: the
+        // launch would then also run ahead of whatever kernel produced its input on the same stream (a device-resident
+        // F-engine -> X-engine chain), which the library cannot see; batches of independent integrations have
+        // clb200_xengine_launch_device_batch instead.
+        static const bool nowait = [] { const char *e = getenv("CLB200_XE_PDL_NOWAIT"); return e && atoi(e); }();
+        p.pdl_nowait = (nowait && x->pdl && !accumulate && !gather) ? 1 : 0;
+    }
     p.gather_epoch = 0;
     for (int r = 0; r < 8; r++) p.gather_flag[r] = nullptr;
     if (gather && x->gather_rank >= 0) {

@@ -377,7 +377,10 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
     __syncthreads();
     tc_fence_after();
     // everything above overlapped the previous grid's tail; from here on global memory is touched
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ... unless this launch neither reads nor accumulates into anything the previous grid writes (plain `=` result,
+    // read-only input): then the CTAs of consecutive integrations simply interleave as SMs free up, and the previous
+    // grid's epilogue and tail overlap this grid's first loads (its completion is still ordered behind the previous one's)
+    if (!p.pdl_nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
     // peers signal each other's mbarriers: those must be initialised cluster-wide before anyone proceeds
     if (clustered) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
