@@ -349,6 +349,23 @@ static void fft_plan_free(orc_fft_plan *p)
     free(p);
 }
 
+/* plans are built once per size and kept, like the reference's fft_complex plan that lives as long as its block
+ * (lib/fft.cc:146-192): a timed per-call loop must not pay for twiddle generation */
+static orc_fft_plan *fft_plan_cached(int n)
+{
+    static orc_fft_plan *cache[32];
+    int logn = 0;
+    while ((1 << logn) < n) logn++;
+    if ((1 << logn) != n || logn >= 32) return NULL;
+    orc_fft_plan *p;
+#pragma omp critical(orc_plan_cache)
+    {
+        if (!cache[logn]) cache[logn] = fft_plan_make(n);
+        p = cache[logn];
+    }
+    return p;
+}
+
 /* in-place on x (interleaved), x already in bit-reversed order; sign=-1 fwd */
 static void fft_exec_bitrev(const orc_fft_plan *p, float *x, int sign)
 {
@@ -393,7 +410,7 @@ static void fft_exec(const orc_fft_plan *p, const float *in, float *out, int sig
 ORC_API int orc_fft_c32(const float *in, float *out, int n, long nvec, int dir,
                         const float *window, int shift)
 {
-    orc_fft_plan *p = fft_plan_make(n);
+    orc_fft_plan *p = fft_plan_cached(n);
     if (!p) return -1;
     int fwd = (dir < 0);
     int h = n / 2;
@@ -428,7 +445,6 @@ ORC_API int orc_fft_c32(const float *in, float *out, int n, long nvec, int dir,
         free(a);
         free(c);
     }
-    fft_plan_free(p);
     return 0;
 }
 
@@ -440,7 +456,7 @@ ORC_API int orc_fft_c32(const float *in, float *out, int n, long nvec, int dir,
  */
 ORC_API int orc_fft_r32(const float *in, float *out, int n, long nvec, const float *window)
 {
-    orc_fft_plan *p = fft_plan_make(n);
+    orc_fft_plan *p = fft_plan_cached(n);
     if (!p) return -1;
     float *a = (float *)malloc(sizeof(float) * 2 * n);
     for (long v = 0; v < nvec; v++) {
@@ -451,7 +467,6 @@ ORC_API int orc_fft_r32(const float *in, float *out, int n, long nvec, const flo
         fft_exec(p, a, out + 2 * (size_t)n * v, -1);
     }
     free(a);
-    fft_plan_free(p);
     return 0;
 }
 

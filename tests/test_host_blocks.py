@@ -36,3 +36,16 @@ def test_driver_fails_loudly_without_a_gpu():
 def test_block_classes_on_gpu():
     r = subprocess.run([os.path.join(LIBDIR, "test_blocks")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_block_layer_thread_safety_under_tsan():
+    """host/test/test_threads.cc built with -fsanitize=thread (make -C gr_clenabled_b200/host tsan): setters from a second
+    thread while work() runs, the X-engine push / pickup / stop path; no ThreadSanitizer report, no wrong output"""
+    exe = os.path.join(LIBDIR, "test_threads_tsan")
+    if not os.path.exists(exe):
+        pytest.skip("TSAN driver not built")
+    env = dict(os.environ, TSAN_OPTIONS="ignore_noninstrumented_modules=1 halt_on_error=0")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "thread test ok" in r.stdout, r.stdout + r.stderr[-2000:]
+    assert "WARNING: ThreadSanitizer" not in r.stderr
