@@ -427,7 +427,10 @@ int fft_launch_big(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_
     if (!sc)
         for (auto &c : f->scratch)
             if (!c.a.p && !sc) sc = &c;
-    if (!sc) sc = &f->scratch[0];
+    if (!sc) {                                        // more launching streams than scratch sets: take over the first one
+        sc = &f->scratch[0];
+        CLB_CUDA(cudaStreamSynchronize(sc->st));      // ... once its owner's work on it is done
+    }
     sc->st = st;
     const size_t bytes = (size_t)nvec * f->n * sizeof(float2);
     CLB_TRY(sc->a.reserve(bytes));

@@ -55,7 +55,6 @@ struct XeParams {
     int split;              // CTAs share channel groups: partial sums meet through int32 atomics
     int nslice;             // > 0: time-sliced decomposition, grid = groups x nslice
     int nbatch;             // integrations back to back in `in` (and matrices in `out`), one grid (TMA kernel, nslice > 0)
-    int dbg;                // timing experiments only (CLB200_XE_DBG): 1 = skip the write-out, 2 = skip the TMEM drain
     int l2_rows;            // prefetch whole (t, station) rows into L2 ahead of the demand loads
     int aligned;            // rows are 4-byte aligned -> 32-bit loads
     float scale;            // 1/127^2 (IChar) or 1/7^2 (packed 4 bit)
@@ -978,8 +977,6 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
     p.nbatch = nbatch;
     {
         const char *e = getenv("CLB200_XE_L2ROWS");
-        static const int dbg = [] { const char *d = getenv("CLB200_XE_DBG"); return d ? atoi(d) : 0; }();
-        p.dbg = dbg;
         p.l2_rows = e ? atoi(e) : 0;      // measured slower on B200 (50.9 vs 44.7 us): off by default
     }
     p.A = x->A;

@@ -531,7 +531,7 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
                 }
             }
             const int f0 = grp_e * FC;
-            if (nstages > 0 && !(p.dbg & 2)) {
+            if (nstages > 0) {
                 const int wq = warp & 3;
                 const int v1 = 8 * wq + ((lane & 15) >> 1), c1 = lane & 1;
                 const int st1 = (NPOL == 1) ? v1 : (v1 >> 1);
@@ -564,13 +564,10 @@ k_xengine_tma(XeParams p, const __grid_constant__ CUtensorMap tmap)
                 tc_fence_before();                                     // TMEM is drained
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(tfree);
-            } else if (nstages > 0) {
-                if (lane == 0) tc_mbar_arrive(tfree);
             }
             if (clustered) break;                                      // the exchange below needs every thread
             tm_worker_sync();
-            if (!(p.dbg & 1))
-                tm_write_out<NPOL>(p, stg, nullptr, 0, 0, spp, npp, f0, min(FC, p.F - f0), tid, (long)kb_e * p.F * npp);
+            tm_write_out<NPOL>(p, stg, nullptr, 0, 0, spp, npp, f0, min(FC, p.F - f0), tid, (long)kb_e * p.F * npp);
             tm_worker_sync();
         }
     }
