@@ -97,6 +97,15 @@ struct clb200_block {
     void set_info(const char *fmt, ...);
     virtual ~clb200_block();
     int init_slots();
+    // Work counters of the persistent kernels (tile_fetch / tile_finish below): one 16-byte record {next tile,
+    // finished CTAs} per launching stream -- launches on one stream are serialised and a kernel's last CTA leaves
+    // its record at zero.  nullptr (more than WORK_CTRS streams, allocation failure, CLB200_STATIC_TILES=1) makes
+    // the kernel fall back to static striding.
+    static constexpr int WORK_CTRS = 8;
+    clb200::Buf work_ctr_buf;
+    cudaStream_t work_ctr_stream[WORK_CTRS] = {};
+    int work_ctr_used = 0;
+    unsigned long long *work_counter(cudaStream_t st);
 };
 
 namespace clb200 {
@@ -302,6 +311,26 @@ int check_kind(clb200_handle h, int kind, T **out)
     *out = static_cast<T *>(h);
     return CLB200_OK;
 }
+
+#ifdef __CUDACC__
+// Dynamic tile assignment for persistent kernels.  Static striding (tile += gridDim.x) lets the hardware's unfair
+// warp scheduling decide when each CTA finishes: ncu shows 10.1 of 12 resident warps active on average in the FFT
+// filter and 14.4 of 16 in the 8192-point FFT -- the early finishers leave their SM under-occupied for the rest of
+// the launch.  A CTA's first tile is blockIdx.x, every further one comes from the counter (fetched one tile ahead,
+// so the atomic's latency hides behind the tile's work); the last CTA to finish zeroes the record.
+__device__ __forceinline__ long tile_fetch(unsigned long long *rec)
+{
+    return (long)gridDim.x + (long)atomicAdd(rec, 1ULL);
+}
+__device__ __forceinline__ void tile_finish(unsigned long long *rec)      // one thread per CTA, after its last fetch
+{
+    __threadfence();
+    if (atomicAdd(rec + 1, 1ULL) == (unsigned long long)gridDim.x - 1) {
+        rec[0] = 0;
+        rec[1] = 0;
+    }
+}
+#endif
 
 inline int grid_for(long work_ctas, int sms, int per_sm)
 {

@@ -33,22 +33,36 @@ __device__ __forceinline__ float4 ld4(const float4 *p) { return __ldcs(p); }
 __device__ __forceinline__ void st4(float4 *p, float4 v) { __stcs(p, v); }
 
 // ---- 1 in -> 1 out over float4 vectors ------------------------------------
+// Tiles of EW_THREADS x EW_UNROLL vectors (16 KiB) handed out by the work counter (common.cuh: tile_fetch; static
+// striding without one): the resident CTAs of an SM then all stay busy until the launch ends.
 template <class F>
 __global__ void __launch_bounds__(EW_THREADS)
-k_map1(const float4 *__restrict__ in, float4 *__restrict__ out, long nvec, long nscalar, F f)
+k_map1(const float4 *__restrict__ in, float4 *__restrict__ out, long nvec, long nscalar, F f, unsigned long long *wq)
 {
-    long stride = (long)gridDim.x * EW_THREADS;
-    long i = (long)blockIdx.x * EW_THREADS + threadIdx.x;
-    for (; i + (EW_UNROLL - 1) * stride < nvec; i += EW_UNROLL * stride) {
+    constexpr long TILE = (long)EW_THREADS * EW_UNROLL;
+    __shared__ long s_next[2];
+    const long ntile = nvec / TILE;
+    int it = 0;
+    for (long tile = blockIdx.x; tile < ntile; it ^= 1) {
+        long nxt = tile + gridDim.x;
+        if (wq != nullptr && threadIdx.x == 0) nxt = tile_fetch(wq);
+        const long i = tile * TILE + threadIdx.x;
         float4 v[EW_UNROLL];
 #pragma unroll
-        for (int u = 0; u < EW_UNROLL; u++) v[u] = ld4(in + i + u * stride);
+        for (int u = 0; u < EW_UNROLL; u++) v[u] = ld4(in + i + u * EW_THREADS);
 #pragma unroll
-        for (int u = 0; u < EW_UNROLL; u++) st4(out + i + u * stride, f.vec(v[u]));
+        for (int u = 0; u < EW_UNROLL; u++) st4(out + i + u * EW_THREADS, f.vec(v[u]));
+        if (wq != nullptr) {
+            if (threadIdx.x == 0) s_next[it] = nxt;
+            __syncthreads();
+            nxt = s_next[it];
+        }
+        tile = nxt;
     }
-    for (; i < nvec; i += stride) st4(out + i, f.vec(ld4(in + i)));
-    // scalar tail (nscalar % 4 floats), first CTA only
+    if (wq != nullptr && threadIdx.x == 0) tile_finish(wq);
+    // the last partial tile, then the scalar tail (nscalar % 4 floats): first CTA only
     if (blockIdx.x == 0) {
+        for (long i = ntile * TILE + threadIdx.x; i < nvec; i += EW_THREADS) st4(out + i, f.vec(ld4(in + i)));
         long t = nvec * 4 + threadIdx.x;
         if (t < nscalar) {
             const float *si = reinterpret_cast<const float *>(in);
@@ -99,7 +113,7 @@ struct Copy {
 };
 
 template <class F>
-int launch_map1(const void *in, void *out, long nfloats, F f, int sms, cudaStream_t st)
+int launch_map1(const void *in, void *out, long nfloats, F f, int sms, cudaStream_t st, clb200_block *blk = nullptr)
 {
     if (nfloats <= 0) return CLB200_OK;
     bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
@@ -107,7 +121,8 @@ int launch_map1(const void *in, void *out, long nfloats, F f, int sms, cudaStrea
         long nvec = nfloats / 4;
         long ctas = (nvec + EW_THREADS * EW_UNROLL - 1) / (EW_THREADS * EW_UNROLL);
         int grid = grid_for(ctas, sms, EW_CTAS_PER_SM);
-        k_map1<F><<<grid, EW_THREADS, 0, st>>>((const float4 *)in, (float4 *)out, nvec, nfloats, f);
+        k_map1<F><<<grid, EW_THREADS, 0, st>>>((const float4 *)in, (float4 *)out, nvec, nfloats, f,
+                                               (blk && ctas > 2L * grid) ? blk->work_counter(st) : nullptr);
     } else {
         long ctas = (nfloats + EW_THREADS - 1) / EW_THREADS;
         int grid = grid_for(ctas, sms, EW_CTAS_PER_SM);
@@ -150,17 +165,30 @@ struct Bin {
 
 __global__ void __launch_bounds__(EW_THREADS)
 k_map2(const float4 *__restrict__ a, const float4 *__restrict__ b, float4 *__restrict__ c,
-       long nvec, Bin f)
+       long nvec, Bin f, unsigned long long *wq)
 {
-    long stride = (long)gridDim.x * EW_THREADS;
-    long i = (long)blockIdx.x * EW_THREADS + threadIdx.x;
-    for (; i + stride < nvec; i += 2 * stride) {
-        float4 a0 = ld4(a + i), a1 = ld4(a + i + stride);
-        float4 b0 = ld4(b + i), b1 = ld4(b + i + stride);
+    constexpr long TILE = (long)EW_THREADS * 2;           // two vectors per operand in flight per thread (8 KiB per operand)
+    __shared__ long s_next[2];
+    const long ntile = nvec / TILE;
+    int it = 0;
+    for (long tile = blockIdx.x; tile < ntile; it ^= 1) {
+        long nxt = tile + gridDim.x;
+        if (wq != nullptr && threadIdx.x == 0) nxt = tile_fetch(wq);
+        const long i = tile * TILE + threadIdx.x;
+        float4 a0 = ld4(a + i), a1 = ld4(a + i + EW_THREADS);
+        float4 b0 = ld4(b + i), b1 = ld4(b + i + EW_THREADS);
         st4(c + i, f.vec(a0, b0));
-        st4(c + i + stride, f.vec(a1, b1));
+        st4(c + i + EW_THREADS, f.vec(a1, b1));
+        if (wq != nullptr) {
+            if (threadIdx.x == 0) s_next[it] = nxt;
+            __syncthreads();
+            nxt = s_next[it];
+        }
+        tile = nxt;
     }
-    for (; i < nvec; i += stride) st4(c + i, f.vec(ld4(a + i), ld4(b + i)));
+    if (wq != nullptr && threadIdx.x == 0) tile_finish(wq);
+    if (blockIdx.x == 0)
+        for (long i = ntile * TILE + threadIdx.x; i < nvec; i += EW_THREADS) st4(c + i, f.vec(ld4(a + i), ld4(b + i)));
 }
 
 // element granularity fallback / tail: `pairs` = process float2 items (complex) else floats
@@ -182,15 +210,16 @@ k_map2_scalar(const float *__restrict__ a, const float *__restrict__ b, float *_
     }
 }
 
-int launch_map2(const void *a, const void *b, void *c, long nfloats, Bin f, int sms, cudaStream_t st)
+int launch_map2(const void *a, const void *b, void *c, long nfloats, Bin f, int sms, cudaStream_t st, clb200_block *blk = nullptr)
 {
     if (nfloats <= 0) return CLB200_OK;
     bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
     long nvec = aligned ? nfloats / 4 : 0;
     if (nvec > 0) {
         long ctas = (nvec + EW_THREADS * 2 - 1) / (EW_THREADS * 2);
-        k_map2<<<grid_for(ctas, sms, EW_CTAS_PER_SM), EW_THREADS, 0, st>>>(
-            (const float4 *)a, (const float4 *)b, (float4 *)c, nvec, f);
+        const int grid = grid_for(ctas, sms, EW_CTAS_PER_SM);
+        k_map2<<<grid, EW_THREADS, 0, st>>>((const float4 *)a, (const float4 *)b, (float4 *)c, nvec, f,
+                                            (blk && ctas > 2L * grid) ? blk->work_counter(st) : nullptr);
     }
     if (nvec * 4 < nfloats) {
         long rest = nfloats - nvec * 4;
@@ -312,20 +341,20 @@ int mathconst_launch(MathConst *m, const void *in, void *out, long nitems, cudaS
     bool is_int = m->dtype == CLB200_DTYPE_INT;
     switch (m->op) {
     case CLB200_OP_MULTIPLY:
-        return is_int ? launch_map1(in, out, nf, ConstI<OpMul>{(int)k}, sms, st)
-                      : launch_map1(in, out, nf, ConstF<OpMul>{k}, sms, st);
+        return is_int ? launch_map1(in, out, nf, ConstI<OpMul>{(int)k}, sms, st, m)
+                      : launch_map1(in, out, nf, ConstF<OpMul>{k}, sms, st, m);
     case CLB200_OP_ADD:
-        return is_int ? launch_map1(in, out, nf, ConstI<OpAdd>{(int)k}, sms, st)
-                      : launch_map1(in, out, nf, ConstF<OpAdd>{k}, sms, st);
+        return is_int ? launch_map1(in, out, nf, ConstI<OpAdd>{(int)k}, sms, st, m)
+                      : launch_map1(in, out, nf, ConstF<OpAdd>{k}, sms, st, m);
     case CLB200_OP_SUBTRACT:
-        return is_int ? launch_map1(in, out, nf, ConstI<OpSub>{(int)k}, sms, st)
-                      : launch_map1(in, out, nf, ConstF<OpSub>{k}, sms, st);
+        return is_int ? launch_map1(in, out, nf, ConstI<OpSub>{(int)k}, sms, st, m)
+                      : launch_map1(in, out, nf, ConstF<OpSub>{k}, sms, st, m);
     case CLB200_OP_COMPLEX_CONJ:
-        return launch_map1(in, out, nf, Conj{}, sms, st);
+        return launch_map1(in, out, nf, Conj{}, sms, st, m);
     case CLB200_OP_EMPTY_W_COPY:
         // the reference's copy case falls through into the multiply (missing break,
         // clMathConst_impl.cc:187-193): not reproduced, this is a copy.
-        return launch_map1(in, out, nf, Copy{}, sms, st);
+        return launch_map1(in, out, nf, Copy{}, sms, st, m);
     default:   // MATHOP_EMPTY: the kernel body is empty, output untouched
         m->n_launch--;
         return CLB200_OK;
@@ -436,7 +465,7 @@ int clb200_mathop_launch_device(clb200_handle h, const void *d_a, const void *d_
     Bin f{m->op, m->dtype == CLB200_DTYPE_COMPLEX, m->dtype == CLB200_DTYPE_INT};
     m->n_launch++;
     return launch_map2(d_a, d_b, d_c, nitems * floats_per_item(m->dtype), f,
-                       device_sm_count(m->device), (cudaStream_t)stream);
+                       device_sm_count(m->device), (cudaStream_t)stream, m);
 }
 
 int clb200_mathop_work(clb200_handle h, const void *a, const void *b, void *c, long nitems)
@@ -459,7 +488,7 @@ int clb200_mathop_work(clb200_handle h, const void *a, const void *b, void *c, l
     return run_chunked(m, pd, nitems, chunk_for(pd),
                        [&](const void **di, void **dout, long n, cudaStream_t st, long *) {
                            m->n_launch++;
-                           return launch_map2(di[0], di[1], dout[0], n * fpi, f, sms, st);
+                           return launch_map2(di[0], di[1], dout[0], n * fpi, f, sms, st, m);
                        });
 }
 

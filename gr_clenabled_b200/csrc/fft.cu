@@ -24,11 +24,12 @@ using namespace clb200::fftdev;
 namespace {
 
 
-// MODE bit 0: inverse (re/im swapped on load and store), bit 1: real input, bit 2: pass-1 twiddles in shared memory
+// MODE bit 0: inverse (re/im swapped on load and store), bit 1: real input, bit 2: pass-1 twiddles in shared memory,
+// bit 3: tiles from the work counter (common.cuh: tile_fetch) instead of static striding
 template <int LOGN, int EPT, int BATCH, int MINB, int MODE>
 __global__ void __launch_bounds__((1 << LOGN) / EPT * BATCH, MINB)
 k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
-      const float2 *__restrict__ tw, const float *__restrict__ win, int shift)
+      const float2 *__restrict__ tw, const float *__restrict__ win, int shift, unsigned long long *wq)
 {
     using P = Plan<LOGN, EPT>;
     constexpr int N = P::N, T = P::T;
@@ -56,7 +57,7 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
     const bool vec_io = one_thread && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
 
     const long ntile = (nvec + BATCH - 1) / BATCH;
-    for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    auto process = [&](long tile) {
         const long v = tile * BATCH + tb;
         const bool active = v < nvec;
         float2 x[EPT];
@@ -130,6 +131,38 @@ k_fft(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
                 __stcs(((c & (N >> 1)) ? dst_dn : dst_up) + c, a);
             });
         }
+    };
+    if constexpr ((MODE & 16) && P::npass() > 1) {
+        // same hand-over, the loop written with the fetch as a run-time choice: ptxas schedules the tile body
+        // differently around it, and which form is faster depends on the size (tools/fft_dyn_ab.py; pick_variant)
+        __shared__ long s_next;
+        const bool dyn = wq != nullptr;
+        for (long tile = blockIdx.x; tile < ntile;) {
+            long nxt = tile + gridDim.x;
+            if (dyn && threadIdx.x == 0) nxt = tile_fetch(wq);
+            process(tile);
+            if (dyn) {
+                if (threadIdx.x == 0) s_next = nxt;
+                __syncthreads();
+                nxt = s_next;
+            }
+            tile = nxt;
+        }
+        if (dyn && threadIdx.x == 0) tile_finish(wq);
+    } else if constexpr ((MODE & 8) && P::npass() > 1) {
+        // the barriers inside fft_core order the hand-over through s_next
+        __shared__ long s_next;
+        for (long tile = blockIdx.x; tile < ntile;) {
+            long nxt = 0;
+            if (threadIdx.x == 0) nxt = tile_fetch(wq);
+            process(tile);
+            if (threadIdx.x == 0) s_next = nxt;
+            __syncthreads();
+            tile = s_next;
+        }
+        if (threadIdx.x == 0) tile_finish(wq);
+    } else {
+        for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) process(tile);
     }
 }
 
@@ -252,10 +285,12 @@ k_fft_pf(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
 struct FftVariant {
     int logn, ept, batch, threads, smem_bytes, tw_total, max_ctas_per_sm;
     void (*fill_tw)(std::vector<float2> &);
-    void (*kernel[3])(const float2 *, float2 *, long, const float2 *, const float *, int);
+    void (*kernel[3])(const float2 *, float2 *, long, const float2 *, const float *, int, unsigned long long *);
     void (*kernel_pf[2])(const float2 *, float2 *, long, const float2 *, const float *, int);   // or null
     void (*kernel_xc)(const float2 *, const float2 *, float *, long, const float2 *);           // FFT correlator
-    void (*kernel_s[2])(const float2 *, float2 *, long, const float2 *, const float *, int);    // pass-1 twiddles in smem
+    void (*kernel_s[2])(const float2 *, float2 *, long, const float2 *, const float *, int, unsigned long long *);    // pass-1 twiddles in smem
+    void (*kernel_d[3])(const float2 *, float2 *, long, const float2 *, const float *, int, unsigned long long *);    // tiles from the work counter (multi-pass sizes) or null
+    void (*kernel_u[3])(const float2 *, float2 *, long, const float2 *, const float *, int, unsigned long long *);    // the same, loop form 2
     int tw1_bytes;
 };
 
@@ -272,6 +307,12 @@ void fill_tw_t(std::vector<float2> &tw)
                 tw[off + (r - 1) * NS + k] = make_float2((float)cos(a), (float)sin(a));
             }
     }
+}
+
+// which work-counter loop form a size uses (0: static striding)
+constexpr int fft_loop_form(int logn)
+{
+    return (logn == 8 || logn == 9 || logn == 12 || logn == 13) ? 1 : logn == 14 ? 2 : 0;
 }
 
 template <int LOGN, int EPT, int BATCH, int MINB>
@@ -292,6 +333,20 @@ FftVariant make_variant()
     v.kernel[2] = &k_fft<LOGN, EPT, BATCH, MINB, 2>;     // forward, real input
     v.kernel_pf[0] = v.kernel_pf[1] = nullptr;
     v.kernel_xc = &k_xcfft<LOGN, EPT, BATCH, MINB>;
+    v.kernel_d[0] = v.kernel_d[1] = v.kernel_d[2] = nullptr;
+    // measured per size on B200 (tools/fft_dyn_ab.py, static striding = 100 %): form 1: 256 points 114 %, 512: 103 %,
+    // 1024: 99 %, 2048: 97 %, 4096: 107 %, 8192: 110 %, 16384: 101 %; form 2: 16384 points 105 %
+    if constexpr (P::npass() > 1 && fft_loop_form(LOGN) == 1) {
+        v.kernel_d[0] = &k_fft<LOGN, EPT, BATCH, MINB, 8>;
+        v.kernel_d[1] = &k_fft<LOGN, EPT, BATCH, MINB, 9>;
+        v.kernel_d[2] = &k_fft<LOGN, EPT, BATCH, MINB, 10>;
+    }
+    v.kernel_u[0] = v.kernel_u[1] = v.kernel_u[2] = nullptr;
+    if constexpr (P::npass() > 1 && fft_loop_form(LOGN) == 2) {
+        v.kernel_u[0] = &k_fft<LOGN, EPT, BATCH, MINB, 16>;
+        v.kernel_u[1] = &k_fft<LOGN, EPT, BATCH, MINB, 17>;
+        v.kernel_u[2] = &k_fft<LOGN, EPT, BATCH, MINB, 18>;
+    }
     v.kernel_s[0] = &k_fft<LOGN, EPT, BATCH, MINB, 4>;
     v.kernel_s[1] = &k_fft<LOGN, EPT, BATCH, MINB, 5>;
     v.tw1_bytes = P::npass() > 1 ? (P::tw_offset(2 < P::npass() ? 2 : P::npass()) - P::tw_offset(1)) * (int)sizeof(float2) : 0;
@@ -337,6 +392,8 @@ struct Fft : clb200_block {
     int resident = 1;     // CTAs per SM the launch is sized for
     bool use_pf = false;  // bulk-copy prefetching kernel available and enabled
     bool use_tw1s = false; // pass-1 twiddles in shared memory (k_fft<.., MODE|4>)
+    bool dyn_ok = false;   // work-counter kernel available with the same occupancy
+    int loop_form = 1;     // which of the two work-counter loop forms (kernel_d / kernel_u)
     // sizes above 16384 (one CTA's shared memory): N = n1 x n2, two passes of the in-SM kernels around transposes
     bool big = false;
     int n1 = 0, n2 = 0;
@@ -460,6 +517,8 @@ int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st
     const FftVariant *v = f->var;
     long ntile = (nvec + v->batch - 1) / v->batch;
     int grid = grid_for(ntile, device_sm_count(f->device), f->resident);
+    // tiles come from the work counter for the sizes that gain from it (fft_loop_form)
+    unsigned long long *wq = (f->dyn_ok && ntile > grid) ? f->work_counter(st) : nullptr;
     // the bulk-copy kernel needs 16 B aligned rows; anything else takes the plain one
     const bool pf = f->use_pf && (((uintptr_t)d_in & 15) == 0);
     if (pf)
@@ -469,11 +528,11 @@ int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st
     else if (f->use_tw1s)
         v->kernel_s[f->mode]<<<grid, v->threads, v->smem_bytes + v->tw1_bytes, st>>>(
             (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
-            f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
+            f->has_window ? (const float *)f->d_win.p : nullptr, f->shift, nullptr);
     else
-        v->kernel[f->mode]<<<grid, v->threads, v->smem_bytes, st>>>(
+        (wq ? (f->loop_form == 2 ? v->kernel_u[f->mode] : v->kernel_d[f->mode]) : v->kernel[f->mode])<<<grid, v->threads, v->smem_bytes, st>>>(
             (const float2 *)d_in, (float2 *)d_out, nvec, (const float2 *)f->d_tw.p,
-            f->has_window ? (const float *)f->d_win.p : nullptr, f->shift);
+            f->has_window ? (const float *)f->d_win.p : nullptr, f->shift, wq);
     CLB_CUDA(cudaGetLastError());
     f->n_launch++;
     return CLB200_OK;
@@ -516,7 +575,7 @@ int xcfft_launch(XcFft *x, const void *const *d_in, void *const *d_out, long nve
         for (int k = 0; k < x->num_inputs; k++) {
             float2 *dst = (float2 *)((char *)x->d_spec.p + per * k);
             v->kernel[0]<<<grid, v->threads, v->smem_bytes, st>>>((const float2 *)d_in[k], dst, nvec,
-                                                                  (const float2 *)x->d_tw.p, nullptr, 0);
+                                                                  (const float2 *)x->d_tw.p, nullptr, 0, nullptr);
             x->n_launch++;
             spec[k] = dst;
         }
@@ -722,6 +781,16 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
         return fail(CLB200_ECUDA);
     }
     f->resident = occ;
+    f->loop_form = fft_loop_form(f->logn);
+    if (f->loop_form) {
+        const void *k = (const void *)(f->loop_form == 2 ? f->var->kernel_u[f->mode] : f->var->kernel_d[f->mode]);
+        int occ2 = 0;
+        if (k && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, f->var->smem_bytes) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k, f->var->threads, f->var->smem_bytes) == cudaSuccess &&
+            occ2 >= occ)
+            f->dyn_ok = true;
+        cudaGetLastError();
+    }
     {
         // pass-1 twiddle table in shared memory (complex modes, tables up to 8 KiB) when it keeps the occupancy
         const char *ts = getenv("CLB200_FFT_TW1S");

@@ -160,6 +160,29 @@ __device__ __forceinline__ void dft_dif(float2 (&x)[NREG])
     });
 }
 
+// In-register forward DFT, radix-2 decimation in TIME: input sample n sits in x[OFF + bitrev(n)], the result is
+// left in natural order (X[k] = x[OFF + k]).  Same operation count and instruction mix as dft_dif (the rotation is
+// applied to the second operand before the add instead of to the difference after it); a DIF pass followed by a DIT
+// pass takes natural-order registers to natural-order registers, so two transforms can run through ONE copy of the
+// code in a loop (the FFT filter's instruction footprint, filter.cu).
+template <int R, int OFF, int NREG>
+__device__ __forceinline__ void dft_dit(float2 (&x)[NREG])
+{
+    constexpr int LR = ilog2(R);
+    static_for<0, LR>([&](auto s_) {
+        constexpr int s = decltype(s_)::value;
+        constexpr int h = 1 << s;
+        static_for<0, R / 2>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            constexpr int g = b / h, i = b % h;
+            constexpr int ia = OFF + g * 2 * h + i, ib = ia + h;
+            float2 a = x[ia], c = mul_w32<i * (16 / h)>(x[ib]);
+            x[ia] = cadd(a, c);
+            x[ib] = csub(a, c);
+        });
+    });
+}
+
 // streaming 64-bit load that does not allocate in L1 (L1 is kept for the twiddle tables)
 __device__ __forceinline__ float2 ldg_stream(const float2 *p)
 {

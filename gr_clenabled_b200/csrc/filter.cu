@@ -41,10 +41,9 @@ __device__ __forceinline__ float2 stream_at(const float2 *__restrict__ hist,
 
 // ---------------------------------------------------------------- FFT filter --
 template <int LOGN, int EPT, int MINB>
-__global__ void __launch_bounds__((1 << LOGN) / EPT, MINB)
-k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_in,
+__device__ __forceinline__ void fftfilt_body(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_in,
           float2 *__restrict__ out, const float2 *__restrict__ H, const float2 *__restrict__ tw,
-          int K, long nblocks, int D, int skip)
+          int K, long nblocks, int D, int skip, long blk0, unsigned long long *wq)
 {
     using P = Plan<LOGN, EPT>;
     constexpr int N = P::N, NPASS = P::npass();
@@ -58,7 +57,11 @@ k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n
     const int km1 = K - 1;
     const int L = N - km1;
 
-    for (long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    // blocks come from the work counter when there is one (common.cuh: tile_fetch), else by static striding
+    __shared__ long s_next;
+    for (long blk = blk0 + blockIdx.x; blk < nblocks;) {
+        long nxt = blk + gridDim.x;
+        if (wq != nullptr && lt == 0) nxt = blk0 + tile_fetch(wq);
         const long base = blk * (long)L;
         float2 x[EPT];
         // interior blocks (no history, no zero fill): plain streaming loads at
@@ -128,7 +131,272 @@ k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n
                 }
             });
         }
+        if (wq != nullptr) {
+            if constexpr (P::T == 32) {
+                nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            } else {
+                if (lt == 0) s_next = nxt;
+                __syncthreads();         // (the barriers inside fft_core keep the next hand-over behind this read)
+                nxt = s_next;
+            }
+        }
+        blk = nxt;
     }
+    if (wq != nullptr && lt == 0) tile_finish(wq);
+}
+
+template <int LOGN, int EPT, int MINB>
+__global__ void __launch_bounds__((1 << LOGN) / EPT, MINB)
+k_fftfilt(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_in,
+          float2 *__restrict__ out, const float2 *__restrict__ H, const float2 *__restrict__ tw,
+          int K, long nblocks, int D, int skip, long blk0, unsigned long long *wq)
+{
+    fftfilt_body<LOGN, EPT, MINB>(hist, in, n_in, out, H, tw, K, nblocks, D, skip, blk0, wq);
+}
+// register-capped instantiations of the one-warp kernel (A/B: CLB200_FILT_MINB = 13 / 14 / 15 -> 152 / 144 / 136 registers)
+template <int LOGN, int EPT, int NREG>
+__global__ void __maxnreg__(NREG)
+k_fftfilt_r(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_in,
+            float2 *__restrict__ out, const float2 *__restrict__ H, const float2 *__restrict__ tw,
+            int K, long nblocks, int D, int skip, long blk0, unsigned long long *wq)
+{
+    fftfilt_body<LOGN, EPT, 1>(hist, in, n_in, out, H, tw, K, nblocks, D, skip, blk0, wq);
+}
+
+// One-warp blocks with the NEXT block's samples fetched ahead of time (interior blocks, 16 B aligned streams):
+//   PF = 1: one lane asks the bulk-copy engine to pull the block into L2 (cp.async.bulk.prefetch.L2) -- the loads of the
+//           next iteration then see L2 latency instead of a loaded HBM's;
+//   PF = 2: one lane starts a bulk copy of the block into a second shared-memory line, completion on an mbarrier;
+//           the first pass reads its inputs with LDS.64 (lanes read 256 contiguous bytes: conflict-free).
+// The profile of the plain kernel (profiles/r2_fftfilt_full.txt) has 18 % of all warp time on the first butterfly
+// waiting for the block's 32 HBM loads (~2600 cycles per block at 3 warps per scheduler).
+template <int LOGN, int EPT, int MINB, int PF>
+__global__ void __launch_bounds__((1 << LOGN) / EPT, MINB)
+k_fftfilt_pf(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_in,
+             float2 *__restrict__ out, const float2 *__restrict__ H, const float2 *__restrict__ tw,
+             int K, long nblocks, int D, int skip, long blk0, unsigned long long *wq)
+{
+    using P = Plan<LOGN, EPT>;
+    constexpr int N = P::N, NPASS = P::npass();
+    constexpr int R0 = P::radix(0), RL = P::radix(NPASS - 1), NSL = P::ns(NPASS - 1);
+    constexpr int LRL = ilog2(RL);
+    static_assert(P::T == 32 && R0 == RL, "one-warp blocks");
+    constexpr uint32_t LINE_BYTES = (N + 2) * (uint32_t)sizeof(float2);
+    extern __shared__ __align__(16) float2 smem[];
+    float2 *line = smem + P::SMEM_F2;                                   // PF == 2: N + 2 samples
+    uint64_t *bar = reinterpret_cast<uint64_t *>(line + N + 2);
+    const int lt = threadIdx.x;
+    const int km1 = K - 1;
+    const int L = N - km1;
+
+    // block b can be fetched ahead when all of [start & ~1, +N+2) lies inside `in`
+    auto ahead_ok = [&](long b) {
+        const long start = b * (long)L - km1;
+        return b < nblocks && start >= 0 && (start & ~1L) + N + 2 <= n_in;
+    };
+    auto issue = [&](long b) {
+        const long start = (b * (long)L - km1) & ~1L;
+        if (lt == 0) {
+            if constexpr (PF == 2) {
+                mbar_expect_tx(bar, LINE_BYTES);
+                bulk_g2s(line, in + start, LINE_BYTES, bar);
+            } else {
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + start), "r"(LINE_BYTES) : "memory");
+            }
+        }
+    };
+    uint32_t parity = 0;
+    if constexpr (PF == 2) {
+        if (lt == 0) mbar_init(bar, 1);
+        __syncwarp();
+    }
+    if (ahead_ok(blk0 + blockIdx.x)) issue(blk0 + blockIdx.x);
+
+    for (long blk = blk0 + blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long base = blk * (long)L;
+        float2 x[EPT];
+        const bool ahead = ahead_ok(blk);
+        const bool interior = base >= km1 && base + N <= n_in + km1;
+        if (PF == 2 && ahead) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            const float2 *src = line + ((base - km1) & 1) + lt;
+            static_for<0, EPT>([&](auto e_) {
+                constexpr int e = decltype(e_)::value;
+                x[e] = src[in_index<P, EPT>(0, e)];
+            });
+            __syncwarp();                                               // every lane has its samples: the line is free
+        } else if (interior) {
+            const float2 *src = in + (base - km1) + lt;
+            static_for<0, EPT>([&](auto e_) {
+                constexpr int e = decltype(e_)::value;
+                x[e] = ldg_stream(src + in_index<P, EPT>(0, e));
+            });
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+                x[e] = stream_at(hist, in, base + in_index<P, EPT>(lt, e), km1, n_in);
+        }
+        if (ahead_ok(blk + gridDim.x)) issue(blk + gridDim.x);
+
+        fft_core<P, EPT, NoHook, 1>(x, smem, lt, tw);
+
+        float2 y[EPT];
+        static_for<0, EPT / RL>([&](auto u_) {
+            constexpr int u = decltype(u_)::value;
+            static_for<0, RL>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const int o = lt + u * P::T + r * NSL;
+                float2 a = cmul(x[u * RL + bitrev(r, LRL)], __ldg(H + o));
+                y[u * RL + r] = make_float2(a.y, a.x);
+            });
+        });
+
+        fft_core<P, EPT, NoHook, 1>(y, smem, lt, tw);
+
+        if (D == 1 && base + L <= n_in) {
+            float2 *dst = out + (base - km1) + lt;
+            for_each_output_c<P, EPT>(y, [&](auto c_, float2 a) {
+                constexpr int c = decltype(c_)::value;
+                if (c + lt >= km1) __stcs(dst + c, make_float2(a.y, a.x));
+            });
+        } else {
+            for_each_output<P, EPT>(y, lt, [&](int n, float2 a) {
+                if (n >= km1) {
+                    long m = base + (n - km1);
+                    if (m < n_in) {
+                        long q = m - skip;
+                        float2 v = make_float2(a.y, a.x);
+                        if (D == 1) {
+                            __stcs(out + q, v);
+                        } else if (q >= 0 && q % D == 0) {
+                            __stcs(out + q / D, v);
+                        }
+                    }
+                }
+            });
+        }
+    }
+}
+
+// ---- the same one-warp 1024-point blocks with HALF the instruction footprint ----------------------------------
+// k_fftfilt's loop body is ~2100 straight-line instructions (33 KB) and every one of an SM's 12 warps walks through
+// it on its own: ncu shows the SM instruction caches missing to the GPC-level cache at 64 % of THAT cache's request
+// peak (gcc__cache_requests_type_instruction; every other kernel of the library: < 1.1 %), and a register-only probe
+// of the same butterfly code falls from 34 to 17 T lane-ops/s once its loop body grows from 30 to 57 KB
+// (tools/src/bfly_probe.cu).  Here both transforms of a block run through ONE copy of the code: pass 0 is a
+// decimation-in-frequency butterfly (natural -> bit-reversed registers), pass 1 a decimation-in-time butterfly
+// (bit-reversed -> natural; the exchange through shared memory permutes for free), so the spectrum comes back in the
+// very register order the next transform starts from and `for (ph = 0; ph < 2; ph++)` needs no register shuffle.
+// Only interior blocks (no history, no ragged end, decimation 1); the caller runs the generic kernel on the edges.
+template <int PF>
+__global__ void __launch_bounds__(32, 12)
+k_fftfilt_1w(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ H,
+             const float2 *__restrict__ tw, int K, long blk0, long blk1, unsigned long long *wq)
+{
+    using P = Plan<10, 32>;
+    constexpr int N = 1024, R = 32;
+    constexpr uint32_t LINE_BYTES = (N + 2) * (uint32_t)sizeof(float2);
+    extern __shared__ __align__(16) float2 smem[];
+    float2 *line = smem + P::SMEM_F2;                                   // PF: N + 2 samples of the next block
+    uint64_t *bar = reinterpret_cast<uint64_t *>(line + N + 2);
+    const int lt = threadIdx.x;
+    const int km1 = K - 1;
+    const int L = N - km1;
+    float2 *const ldp = smem + P::pad(lt);
+    float2 *const stp = smem + P::pad(lt * R);
+    const float2 *const twp = tw + lt;
+    const float2 *const Hp = H + lt;
+
+    auto issue = [&](long b) {
+        if (lt == 0) {
+            mbar_expect_tx(bar, LINE_BYTES);
+            bulk_g2s(line, in + ((b * (long)L - km1) & ~1L), LINE_BYTES, bar);
+        }
+    };
+    uint32_t parity = 0;
+    if constexpr (PF) {
+        if (lt == 0) mbar_init(bar, 1);
+        __syncwarp();
+        if (blk0 + blockIdx.x < blk1) issue(blk0 + blockIdx.x);
+    }
+
+    long nxt = blk0 + blockIdx.x + gridDim.x;                // PF: the block after the one in flight
+    if (PF && wq != nullptr) {
+        if (lt == 0) nxt = blk0 + tile_fetch(wq);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    for (long blk = blk0 + blockIdx.x; blk < blk1;) {
+        if (!PF) {
+            nxt = blk + gridDim.x;
+            if (wq != nullptr && lt == 0) nxt = blk0 + tile_fetch(wq);
+        }
+        const long start = blk * (long)L - km1;              // first stream sample of the block (>= 0 for these blocks)
+        float2 x[R];
+        if constexpr (PF) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            const float2 *src = line + (start & 1) + lt;
+            static_for<0, R>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                x[r] = src[r * 32];
+            });
+            __syncwarp();                                    // every lane has its samples: the line is free again
+            if (nxt < blk1) issue(nxt);
+        } else {
+            const float2 *src = in + start + lt;
+            static_for<0, R>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                x[r] = ldg_stream(src + r * 32);
+            });
+        }
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ph++) {
+            // pass 0: x[r] = element lt + 32 r  ->  X0[k] in x[bitrev(k)]  ->  shared memory [lt * 32 + k]
+            dft_dif<R, 0>(x);
+            __syncwarp();                                    // the previous transform's pass-1 reads are done
+            static_for<0, R / 2>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                const float2 a = x[bitrev(2 * q, 5)], b = x[bitrev(2 * q + 1, 5)];
+                *reinterpret_cast<float4 *>(stp + P::pad(2 * q)) = make_float4(a.x, a.y, b.x, b.y);
+            });
+            __syncwarp();
+            // pass 1: element lt + 32 r, times W_1024^(r * lt), into the slot a decimation-in-time butterfly wants
+            static_for<0, R>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const float2 v = ldp[P::pad(r * 32)];
+                if constexpr (r == 0) x[0] = v;
+                else x[bitrev(r, 5)] = cmul(v, __ldg(twp + (r - 1) * 32));
+            });
+            dft_dit<R, 0>(x);                                // x[r] = element lt + 32 r of the transform
+            if (ph == 0) {
+                // spectrum * H; re/im swapped: the second round is the inverse transform (forward on swapped data)
+                static_for<0, R>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    const float2 a = cmul(x[r], __ldg(Hp + r * 32));
+                    x[r] = make_float2(a.y, a.x);
+                });
+            }
+        }
+        float2 *dst = out + start + lt;
+        static_for<0, R>([&](auto r_) {
+            constexpr int r = decltype(r_)::value;
+            if (r * 32 + lt >= km1) __stcs(dst + r * 32, make_float2(x[r].y, x[r].x));
+        });
+        if constexpr (PF) {
+            // the next block's copy is in flight; fetch the one after it
+            blk = nxt;
+            nxt = blk + gridDim.x;
+            if (wq != nullptr) {
+                if (lt == 0) nxt = blk0 + tile_fetch(wq);
+                nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            }
+        } else {
+            if (wq != nullptr) nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            blk = nxt;
+        }
+    }
+    if (wq != nullptr && lt == 0) tile_finish(wq);
 }
 
 // ------------------------------------------------------------ time-domain FIR --
@@ -142,15 +410,18 @@ __host__ __device__ constexpr int fir_pad(int i) { return i + (i >> 3); }
 // the input tile in shared memory
 __global__ void __launch_bounds__(FIR_THREADS)
 k_fir_d1(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_in,
-         float2 *__restrict__ out, const float *__restrict__ rtaps, int K, int K8)
+         float2 *__restrict__ out, const float *__restrict__ rtaps, int K, int K8, unsigned long long *wq)
 {
+    __shared__ long s_next;
     extern __shared__ __align__(16) unsigned char fir_smem[];
     float *s_t = reinterpret_cast<float *>(fir_smem);                     // K8 floats
     float2 *s_x = reinterpret_cast<float2 *>(fir_smem + (size_t)K8 * 4);  // fir_pad(TILE + K8)
     const int km1 = K - 1;
     for (int i = threadIdx.x; i < K8; i += FIR_THREADS) s_t[i] = rtaps[i];
     const long ntile = (n_in + FIR_TILE - 1) / FIR_TILE;
-    for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    for (long tile = blockIdx.x; tile < ntile;) {
+        long nxt = tile + gridDim.x;                      // tiles from the work counter (common.cuh) when there is one
+        if (wq != nullptr && threadIdx.x == 0) nxt = tile_fetch(wq);
         const long g0 = tile * FIR_TILE;
         __syncthreads();
         for (int i = threadIdx.x; i < FIR_TILE + K8; i += FIR_THREADS)
@@ -182,7 +453,14 @@ k_fir_d1(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_
 #pragma unroll
         for (int j = 0; j < FIR_OPT; j++)
             if (g0 + o0 + j < n_in) __stcs(out + g0 + o0 + j, acc[j]);
+        if (wq != nullptr) {
+            if (threadIdx.x == 0) s_next = nxt;
+            __syncthreads();        // (the two barriers of the next tile's load keep its hand-over behind this read)
+            nxt = s_next;
+        }
+        tile = nxt;
     }
+    if (wq != nullptr && threadIdx.x == 0) tile_finish(wq);
 }
 
 // any decimation: one output per thread, taps in shared memory
@@ -221,12 +499,14 @@ __global__ void k_hist_update(const float2 *__restrict__ hist, const float2 *__r
 
 // ---------------------------------------------------------------------- host --
 typedef void (*fftfilt_kernel_t)(const float2 *, const float2 *, long, float2 *, const float2 *,
-                                 const float2 *, int, long, int, int);
+                                 const float2 *, int, long, int, int, long, unsigned long long *);
 
 struct FiltVariant {
     int logn, threads, smem_bytes;
     void (*fill_tw)(std::vector<float2> &);
     fftfilt_kernel_t kernel;
+    fftfilt_kernel_t kernel_pf[2] = {nullptr, nullptr};   // one-warp blocks: next block prefetched to L2 / into shared memory
+    int smem_pf[2] = {0, 0};
 };
 
 template <int LOGN, int EPT>
@@ -248,8 +528,14 @@ template <int LOGN, int EPT, int MINB>
 FiltVariant make_filt()
 {
     using P = Plan<LOGN, EPT>;
-    return FiltVariant{LOGN, P::T, P::SMEM_F2 * (int)sizeof(float2), &fill_tw_f<LOGN, EPT>,
-                       &k_fftfilt<LOGN, EPT, MINB>};
+    FiltVariant v{LOGN, P::T, P::SMEM_F2 * (int)sizeof(float2), &fill_tw_f<LOGN, EPT>, &k_fftfilt<LOGN, EPT, MINB>};
+    if constexpr (P::T == 32 && P::npass() == 2) {
+        v.kernel_pf[0] = &k_fftfilt_pf<LOGN, EPT, MINB, 1>;
+        v.kernel_pf[1] = &k_fftfilt_pf<LOGN, EPT, MINB, 2>;
+        v.smem_pf[0] = v.smem_bytes;
+        v.smem_pf[1] = v.smem_bytes + (P::N + 2) * (int)sizeof(float2) + 16;
+    }
+    return v;
 }
 
 // block FFT size by tap count: keep L = NF-K+1 >= NF/2 so at most half of every
@@ -259,6 +545,10 @@ const FiltVariant *pick_filt(int ntaps)
     static const FiltVariant v10 = make_filt<10, 32, 12>();   // 1024 = 32^2: one warp per block, 1 exchange per FFT
                                                               // (12 CTAs/SM, 170 regs: 3.15 TB/s vs 2.76 for 4096 at 256 taps)
     static const FiltVariant v10b = make_filt<10, 32, 16>();  // same, capped at 128 registers (A/B: CLB200_FILT_MINB=16)
+    static FiltVariant v10c = make_filt<10, 32, 12>(), v10d = make_filt<10, 32, 12>(), v10e = make_filt<10, 32, 12>();
+    v10c.kernel = &k_fftfilt_r<10, 32, 152>;
+    v10d.kernel = &k_fftfilt_r<10, 32, 144>;
+    v10e.kernel = &k_fftfilt_r<10, 32, 136>;
     static const FiltVariant v12 = make_filt<12, 16, 2>();    // 4096 = 16^3 (register hand-over)
     static const FiltVariant v14 = make_filt<14, 16, 1>();    // 16384 = 16^3 * 4
     const char *e = getenv("CLB200_FILT_NF");                 // tuning: force the block size
@@ -267,7 +557,8 @@ const FiltVariant *pick_filt(int ntaps)
     if (force == 4096 && ntaps <= 4096) return &v12;
     if (ntaps <= 513 && force == 0) {
         const char *mb = getenv("CLB200_FILT_MINB");
-        return (mb && atoi(mb) == 16) ? &v10b : &v10;
+        const int m = mb ? atoi(mb) : 0;
+        return m == 16 ? &v10b : m == 15 ? &v10e : m == 14 ? &v10d : m == 13 ? &v10c : &v10;
     }
     if (ntaps <= 2049) return &v12;
     if (ntaps <= 8193) return &v14;
@@ -285,6 +576,8 @@ struct Filter : clb200_block {
     int skip = 0;                       // decimation phase: inputs to drop before the next output
     int k8 = 0;
     int resident = 1;
+    int pf = 0, resident_pf = 1;        // prefetching one-warp kernel (0: off, 1: L2, 2: shared memory) and its occupancy
+    int compact = 0, resident_c = 1, smem_c = 0;   // compact one-warp kernel k_fftfilt_1w (1: plain loads, 2: bulk-copy prefetch)
     cudaEvent_t hist_ready = nullptr;
     bool hist_pending = false;
     ~Filter() override
@@ -373,6 +666,37 @@ int filter_configure(Filter *f, const std::vector<float> &taps)
                                                                f->var->threads, f->var->smem_bytes));
         CLB_CHECK(occ >= 1, CLB200_ECUDA, "clFilter: FFT-filter kernel does not fit an SM");
         f->resident = occ;
+        f->compact = 0;
+        if (f->var->logn == 10 && f->var->threads == 32) {
+            const char *ce = getenv("CLB200_FILT_COMPACT");
+            const int wantc = ce ? atoi(ce) : 0;      // opt-in (measured on par with the generic kernel)
+            if (wantc == 1 || wantc == 2) {
+                const void *k = wantc == 2 ? (const void *)k_fftfilt_1w<1> : (const void *)k_fftfilt_1w<0>;
+                const int sm = f->var->smem_bytes + (wantc == 2 ? (1024 + 2) * (int)sizeof(float2) + 16 : 0);
+                int occ2 = 0;
+                if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) == cudaSuccess &&
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k, 32, sm) == cudaSuccess && occ2 >= 1) {
+                    f->compact = wantc;
+                    f->resident_c = occ2;
+                    f->smem_c = sm;
+                }
+                cudaGetLastError();
+            }
+        }
+        f->pf = 0;
+        const char *pe = getenv("CLB200_FILT_PF");
+        const int want = pe ? atoi(pe) : 0;
+        if ((want == 1 || want == 2) && f->var->kernel_pf[want - 1]) {
+            const void *k = (const void *)f->var->kernel_pf[want - 1];
+            int occ2 = 0;
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, f->var->smem_pf[want - 1]) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k, f->var->threads, f->var->smem_pf[want - 1]) == cudaSuccess &&
+                occ2 >= 1) {
+                f->pf = want;
+                f->resident_pf = occ2;
+            }
+            cudaGetLastError();
+        }
     }
     if (f->time_kernel)
         f->set_info("clFilter %d taps, decimation %d: time-domain k_fir_d1 (register sliding window, taps + %d-sample tile in shared "
@@ -415,7 +739,8 @@ int filter_launch(Filter *f, const float2 *d_in, long n_in, float2 *d_out, long 
                 long ntile = (n_in + FIR_TILE - 1) / FIR_TILE;
                 size_t smem = (size_t)f->k8 * 4 + sizeof(float2) * fir_pad(FIR_TILE + f->k8 + 8);
                 k_fir_d1<<<grid_for(ntile, sms, f->resident), FIR_THREADS, smem, st>>>(
-                    hist, d_in, n_in, d_out, (const float *)f->d_rtaps.p, K, f->k8);
+                    hist, d_in, n_in, d_out, (const float *)f->d_rtaps.p, K, f->k8,
+                    ntile > (long)sms * f->resident ? f->work_counter(st) : nullptr);
             } else {
                 long ctas = (nout + FIR_THREADS - 1) / FIR_THREADS;
                 k_fir_dec<<<grid_for(ctas, sms, 8), FIR_THREADS, f->k8 * 4, st>>>(
@@ -424,11 +749,39 @@ int filter_launch(Filter *f, const float2 *d_in, long n_in, float2 *d_out, long 
         } else {
             const int NF = 1 << f->var->logn, L = NF - km1;
             long nblocks = (n_in + L - 1) / L;
-            f->var->kernel<<<grid_for(nblocks, sms, f->resident), f->var->threads,
-                             f->var->smem_bytes, st>>>(hist, d_in, n_in, d_out,
-                                                      (const float2 *)f->d_H.p,
-                                                      (const float2 *)f->d_tw.p, K, nblocks, D,
-                                                      f->skip);
+            const float2 *dH = (const float2 *)f->d_H.p, *dtw = (const float2 *)f->d_tw.p;
+            // one-warp 1024-point blocks, decimation 1: the compact kernel takes the interior blocks
+            //   b*L - (K-1) >= 0  and  b*L - (K-1) + NF (+ 2 with the bulk-copy prefetch) <= n_in,
+            // the generic kernel the (at most three) blocks at the two ends of the call
+            long b0 = 0, b1 = 0;
+            unsigned long long *wq = nullptr;
+            if (f->compact && D == 1) {
+                const int slack = f->compact == 2 ? 2 : 0;
+                b0 = (km1 + L - 1) / L;
+                b1 = n_in - NF - slack + km1 >= 0 ? (n_in - NF - slack + km1) / L + 1 : 0;
+                b1 = std::min(b1, nblocks);
+                if (f->compact == 2 && ((uintptr_t)d_in & 15) != 0) b1 = b0;      // bulk copies need 16 B aligned streams
+            }
+            if (b1 > b0) {
+                if (b1 - b0 > (long)sms * f->resident_c) wq = f->work_counter(st);
+                if (f->compact == 2)
+                    k_fftfilt_1w<1><<<grid_for(b1 - b0, sms, f->resident_c), 32, f->smem_c, st>>>(d_in, d_out, dH, dtw, K, b0, b1, wq);
+                else
+                    k_fftfilt_1w<0><<<grid_for(b1 - b0, sms, f->resident_c), 32, f->smem_c, st>>>(d_in, d_out, dH, dtw, K, b0, b1, wq);
+                f->n_launch++;
+                if (b0 > 0)
+                    f->var->kernel<<<grid_for(b0, sms, f->resident), f->var->threads, f->var->smem_bytes, st>>>(
+                        hist, d_in, n_in, d_out, dH, dtw, K, b0, D, f->skip, 0, nullptr);
+                if (b1 < nblocks)
+                    f->var->kernel<<<grid_for(nblocks - b1, sms, f->resident), f->var->threads, f->var->smem_bytes, st>>>(
+                        hist, d_in, n_in, d_out, dH, dtw, K, nblocks, D, f->skip, b1, nullptr);
+            } else if (f->pf && ((uintptr_t)d_in & 15) == 0)
+                f->var->kernel_pf[f->pf - 1]<<<grid_for(nblocks, sms, f->resident_pf), f->var->threads,
+                                               f->var->smem_pf[f->pf - 1], st>>>(hist, d_in, n_in, d_out, dH, dtw, K, nblocks, D, f->skip, 0, nullptr);
+            else
+                f->var->kernel<<<grid_for(nblocks, sms, f->resident), f->var->threads, f->var->smem_bytes, st>>>(
+                    hist, d_in, n_in, d_out, dH, dtw, K, nblocks, D, f->skip, 0,
+                    nblocks > (long)sms * f->resident ? f->work_counter(st) : nullptr);
         }
         CLB_CUDA(cudaGetLastError());
         f->n_launch++;

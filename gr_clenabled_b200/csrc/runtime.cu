@@ -136,9 +136,32 @@ int clb200_block::init_slots()
     return CLB200_OK;
 }
 
+unsigned long long *clb200_block::work_counter(cudaStream_t st)
+{
+    const char *e = getenv("CLB200_STATIC_TILES");      // A/B switch, read per launch
+    if (e && atoi(e) != 0) return nullptr;
+    if (!work_ctr_buf.p) {
+        if (work_ctr_buf.reserve(16 * WORK_CTRS) != CLB200_OK) return nullptr;
+        if (cudaMemset(work_ctr_buf.p, 0, 16 * WORK_CTRS) != cudaSuccess) {
+            cudaGetLastError();
+            work_ctr_buf.release();
+            return nullptr;
+        }
+    }
+    int i = 0;
+    for (; i < work_ctr_used; i++)
+        if (work_ctr_stream[i] == st) break;
+    if (i == work_ctr_used) {
+        if (work_ctr_used == WORK_CTRS) return nullptr;
+        work_ctr_stream[work_ctr_used++] = st;
+    }
+    return reinterpret_cast<unsigned long long *>(work_ctr_buf.p) + 2 * i;
+}
+
 clb200_block::~clb200_block()
 {
     DeviceGuard g(device);
+    work_ctr_buf.release();
     for (int i = 0; i < NSLOT; i++) {
         Slot &s = slot[i];
         if (s.stream) cudaStreamSynchronize(s.stream);

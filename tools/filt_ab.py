@@ -1,4 +1,5 @@
-"""FFT-filter A/B (256 taps, 64 Mi samples device-resident): register cap / block-size variants."""
+"""FFT-filter A/B (256 taps, 64 Mi samples device-resident): kernel variants selected by environment switches.
+Every variant's output is compared with the first one's (max abs difference)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,11 +10,16 @@ n = 1 << 26
 a = torch.empty(n * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
 b = torch.empty(n * 2, dtype=torch.float32, device="cuda")
 taps = np.zeros(256, np.float32); taps[:255] = orc.firdes_low_pass_hamming(1.0, 30e6, 1.5e6, 283000.0)
+KEYS = ("CLB200_FILT_MINB", "CLB200_FILT_NF", "CLB200_FILT_PF", "CLB200_FILT_COMPACT")
+variants = [("base", {})]
+for spec in sys.argv[1:]:
+    variants.append((spec, dict(kv.split("=") for kv in spec.split(","))))
+variants.append(("base again", {}))
 ref = None
-for tag, env in (("168 regs, 12 warps/SM", {}), ("128 regs, 16 warps/SM", {"CLB200_FILT_MINB": "16"}), ("NF=4096", {"CLB200_FILT_NF": "4096"}),
-                 ("168 regs, 12 warps/SM", {}), ("128 regs, 16 warps/SM", {"CLB200_FILT_MINB": "16"})):
-    for k in ("CLB200_FILT_MINB", "CLB200_FILT_NF"): os.environ.pop(k, None)
-    os.environ.update(env)
+for tag, env in variants:
+    for k in KEYS: os.environ.pop(k, None)
+    os.environ.pop("CLB200_STATIC_TILES", None)
+    os.environ.update({("CLB200_STATIC_TILES" if k == "STATIC" else "CLB200_FILT_" + k): v for k, v in env.items()})
     blk = blocks.clFilter(1, 1, 0, 0, 1, taps, 1, 0, False)
     for _ in range(2): blk.launch_device(a.data_ptr(), n, b.data_ptr(), sp)
     torch.cuda.synchronize()
@@ -22,4 +28,9 @@ for tag, env in (("168 regs, 12 warps/SM", {}), ("128 regs, 16 warps/SM", {"CLB2
     for _ in range(5): blk.launch_device(a.data_ptr(), n, b.data_ptr(), sp)
     e1.record(); torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 5 / 1e3
-    print("%-26s %.1f GB/s  (%.1f Gsamples/s)" % (tag, 16 * n / t / 1e9, n / t / 1e9), flush=True)
+    # a fresh block (zero history) for the comparison run
+    blk2 = blocks.clFilter(1, 1, 0, 0, 1, taps, 1, 0, False)
+    b.zero_(); blk2.launch_device(a.data_ptr(), n, b.data_ptr(), sp); torch.cuda.synchronize()
+    if ref is None: ref = b.clone(); d = 0.0
+    else: d = float((b - ref).abs().max())
+    print("%-28s %.1f GB/s  (%.1f Gsamples/s)  maxdiff vs base %.2e" % (tag, 16 * n / t / 1e9, n / t / 1e9, d), flush=True)
