@@ -429,14 +429,20 @@ k_fir_d1(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_
         __syncthreads();
         const int o0 = threadIdx.x * FIR_OPT;
         float2 acc[FIR_OPT], w[2 * FIR_OPT];
+        // o0 and the tap index advance in steps of 8, so fir_pad() is linear along the walk: 9 slots per 8 samples.
+        // One pointer bump per step and immediate offsets instead of a shift-and-add per load (the loop was 128 FFMA
+        // in ~180 instructions); two steps per iteration so that the window hand-over is a renaming, not 16 MOVs.
+        const float2 *wp = s_x + fir_pad(o0);
 #pragma unroll
         for (int j = 0; j < FIR_OPT; j++) {
             acc[j] = make_float2(0.f, 0.f);
-            w[j] = s_x[fir_pad(o0 + j)];
+            w[j] = wp[j];
         }
+#pragma unroll 2
         for (int i = 0; i < K8; i += FIR_OPT) {
+            wp += FIR_OPT + 1;
 #pragma unroll
-            for (int j = 0; j < FIR_OPT; j++) w[FIR_OPT + j] = s_x[fir_pad(o0 + i + FIR_OPT + j)];
+            for (int j = 0; j < FIR_OPT; j++) w[FIR_OPT + j] = wp[j];
             const float4 t0 = *reinterpret_cast<const float4 *>(s_t + i);
             const float4 t1 = *reinterpret_cast<const float4 *>(s_t + i + 4);
             const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};

@@ -1,2 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 600 python bench.py > gpurun_out/bench_dyn.json 2> gpurun_out/bench_dyn.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_dyn.err
+timeout 100 python tools/fir_ab.py 2>&1 | tail -1
+CLB200_FIR_CTAS=4 timeout 100 python tools/fir_ab.py 2>&1 | tail -1
+CLB200_FIR_CTAS=6 timeout 100 python tools/fir_ab.py 2>&1 | tail -1
+CLB200_FIR_CTAS=8 timeout 100 python tools/fir_ab.py 2>&1 | tail -1
+timeout 300 python -m pytest tests -m gpu -x -q -k "filter or Filter or fir or dynamic" 2>&1 | tail -3
