@@ -396,6 +396,10 @@ struct Fft : clb200_block {
     int loop_form = 1;     // which of the two work-counter loop forms (kernel_d / kernel_u)
     // sizes above 16384 (one CTA's shared memory): N = n1 x n2, two passes of the in-SM kernels around transposes
     bool big = false;
+    // sizes that are not a power of two: chirp-z (Bluestein) on top of two power-of-two plans of m >= 2n-1 points
+    bool blue = false;
+    int m = 0;
+    Buf d_chirp, d_bspec;        // w[n] = e^{-i pi n^2 / N} (n floats2), FFT_m of the wrapped conj(w), pre-scaled by 1/m
     int n1 = 0, n2 = 0;
     clb200_handle sub1 = nullptr, sub2 = nullptr;      // n1- and n2-point plans (complex, no window, no shift)
     struct Scratch {
@@ -407,6 +411,8 @@ struct Fft : clb200_block {
         DeviceGuard g(device);
         d_tw.release();
         d_win.release();
+        d_chirp.release();
+        d_bspec.release();
         for (auto &sc : scratch) {
             sc.a.release();
             sc.b.release();
@@ -476,7 +482,92 @@ __global__ void __launch_bounds__(256) k_fft_tr(const void *__restrict__ in, flo
 
 int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st);
 
-int fft_launch_big(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
+// ---- sizes that are not a power of two: Bluestein ------------------------------------------------------------
+// clFFT plans accept any 2^a 3^b 5^c 7^d length (lib/clFFT_impl.cc:97-100 hands fftSize straight to
+// clfftCreateDefaultPlan); here ANY length runs as a chirp-z transform over the power-of-two kernels:
+//   n k = (n^2 + k^2 - (k - n)^2) / 2   =>   X[k] = w[k] * sum_n (x[n] w[n]) conj(w)[k - n],   w[n] = e^{-i pi n^2 / N}
+// i.e. one circular convolution of length m >= 2N - 1 (m a power of two):  pre-multiply + zero-pad, FFT_m, multiply by
+// the resident spectrum of the wrapped conj(w) (pre-scaled by 1/m), inverse FFT_m, post-multiply.  The backward
+// transform is conj(DFT(conj x)).  Window, real input and the half swaps of the reference (vlen_2 = N / 2: an odd
+// length leaves its last element in place, lib/clFFT_impl.cc:81,548-553,594-607) are fused into the two
+// element-wise kernels.  Functional completeness (about ten passes over HBM), not a roofline kernel.
+__device__ __forceinline__ int blue_swap(int p, int h)       // position p of a buffer whose halves [0,h) [h,2h) are swapped
+{
+    return p < h ? p + h : (p < 2 * h ? p - h : p);
+}
+
+__global__ void __launch_bounds__(256) k_blue_pre(const void *__restrict__ in, float2 *__restrict__ a, long nvec, int n, int m,
+                                                  const float2 *__restrict__ chirp, const float *__restrict__ win, int real_in,
+                                                  int inverse, int swap_h)
+{
+    const long total = nvec * (long)m;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long v = i / m;
+        const int j = (int)(i - v * m);
+        float2 val = make_float2(0.f, 0.f);
+        if (j < n) {
+            const int src = swap_h ? blue_swap(j, swap_h) : j;
+            val = real_in ? make_float2(reinterpret_cast<const float *>(in)[v * n + src], 0.f)
+                          : reinterpret_cast<const float2 *>(in)[v * n + src];
+            if (win != nullptr) {
+                const float w = win[j];
+                val.x *= w;
+                val.y *= w;
+            }
+            if (inverse) val.y = -val.y;
+            val = cmul(val, chirp[j]);
+        }
+        a[i] = val;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_blue_mul(float2 *__restrict__ a, long total, int m, const float2 *__restrict__ bspec)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        a[i] = cmul(a[i], bspec[i & (m - 1)]);
+}
+
+__global__ void __launch_bounds__(256) k_blue_post(const float2 *__restrict__ c, float2 *__restrict__ out, long nvec, int n, int m,
+                                                   const float2 *__restrict__ chirp, int inverse, int swap_h)
+{
+    const long total = nvec * (long)n;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long v = i / n;
+        const int k = (int)(i - v * n);
+        float2 val = cmul(c[v * m + k], chirp[k]);
+        if (inverse) val.y = -val.y;
+        out[v * n + (swap_h ? blue_swap(k, swap_h) : k)] = val;
+    }
+}
+
+Fft::Scratch *fft_scratch(Fft *f, cudaStream_t st, size_t bytes, int *rc);
+
+int fft_launch_blue(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
+{
+    int rc = CLB200_OK;
+    Fft::Scratch *sc = fft_scratch(f, st, (size_t)nvec * f->m * sizeof(float2), &rc);
+    if (!sc) return rc;
+    float2 *ta = (float2 *)sc->a.p, *tb = (float2 *)sc->b.p;
+    const int N = f->n, M = f->m, h = N / 2;
+    const int inverse = f->dir > 0;
+    const long tot_m = nvec * (long)M, tot_n = nvec * (long)N;
+    const int sms = device_sm_count(f->device);
+    auto grid = [&](long total) { return (int)std::max<long>(1, std::min<long>((total + 255) / 256, (long)sms * 8)); };
+    k_blue_pre<<<grid(tot_m), 256, 0, st>>>(d_in, ta, nvec, N, M, (const float2 *)f->d_chirp.p,
+                                            f->has_window ? (const float *)f->d_win.p : nullptr, f->dtype == CLB200_DTYPE_FLOAT,
+                                            inverse, (f->shift && inverse) ? h : 0);
+    CLB_TRY(fft_launch(static_cast<Fft *>(f->sub1), ta, tb, nvec, st));
+    k_blue_mul<<<grid(tot_m), 256, 0, st>>>(tb, tot_m, M, (const float2 *)f->d_bspec.p);
+    CLB_TRY(fft_launch(static_cast<Fft *>(f->sub2), tb, ta, nvec, st));
+    k_blue_post<<<grid(tot_n), 256, 0, st>>>(ta, (float2 *)d_out, nvec, N, M, (const float2 *)f->d_chirp.p, inverse,
+                                             (f->shift && !inverse) ? h : 0);
+    CLB_CUDA(cudaGetLastError());
+    f->n_launch += 3;
+    return CLB200_OK;
+}
+
+// the two scratch buffers of the launching stream, grown to `bytes` each
+Fft::Scratch *fft_scratch(Fft *f, cudaStream_t st, size_t bytes, int *rc)
 {
     Fft::Scratch *sc = nullptr;
     for (auto &c : f->scratch)
@@ -486,12 +577,22 @@ int fft_launch_big(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_
             if (!c.a.p && !sc) sc = &c;
     if (!sc) {                                        // more launching streams than scratch sets: take over the first one
         sc = &f->scratch[0];
-        CLB_CUDA(cudaStreamSynchronize(sc->st));      // ... once its owner's work on it is done
+        if (cudaStreamSynchronize(sc->st) != cudaSuccess) {      // ... once its owner's work on it is done
+            set_error("clFFT: scratch takeover failed");
+            *rc = CLB200_ECUDA;
+            return nullptr;
+        }
     }
     sc->st = st;
-    const size_t bytes = (size_t)nvec * f->n * sizeof(float2);
-    CLB_TRY(sc->a.reserve(bytes));
-    CLB_TRY(sc->b.reserve(bytes));
+    if ((*rc = sc->a.reserve(bytes)) != CLB200_OK || (*rc = sc->b.reserve(bytes)) != CLB200_OK) return nullptr;
+    return sc;
+}
+
+int fft_launch_big(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
+{
+    int src = CLB200_OK;
+    Fft::Scratch *sc = fft_scratch(f, st, (size_t)nvec * f->n * sizeof(float2), &src);
+    if (!sc) return src;
     float2 *ta = (float2 *)sc->a.p, *tb = (float2 *)sc->b.p;
     const int N1 = f->n1, N2 = f->n2, half = f->n >> 1;
     const int gz = (int)std::min<long>(nvec, 64);
@@ -513,6 +614,7 @@ int fft_launch_big(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_
 int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
 {
     if (nvec <= 0) return CLB200_OK;
+    if (f->blue) return fft_launch_blue(f, d_in, d_out, nvec, st);
     if (f->big) return fft_launch_big(f, d_in, d_out, nvec, st);
     const FftVariant *v = f->var;
     long ntile = (nvec + v->batch - 1) / v->batch;
@@ -689,8 +791,9 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
                       int device, int shift, clb200_handle *out)
 {
     CLB_CHECK(out != nullptr, CLB200_EINVAL, "null out");
-    CLB_CHECK(fft_size >= 2 && (fft_size & (fft_size - 1)) == 0 && fft_size <= (1 << 22), CLB200_EINVAL,
-              "clFFT: fft size %d is not a power of two in 2..4194304", fft_size);
+    const bool pow2 = fft_size >= 2 && (fft_size & (fft_size - 1)) == 0;
+    CLB_CHECK(fft_size >= 2 && fft_size <= (pow2 ? (1 << 22) : (1 << 21)), CLB200_EINVAL,
+              "clFFT: fft size %d is outside 2..4194304 (powers of two) / 2..2097152 (other lengths)", fft_size);
     CLB_CHECK(dir == CLB200_FFT_FORWARD || dir == CLB200_FFT_BACKWARD, CLB200_EINVAL,
               "clFFT: direction must be -1 (forward) or 1 (backward), got %d", dir);
     // lib/clFFT_impl.cc:74-76: "window not the same length as fft_size"
@@ -720,6 +823,80 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
         delete f;
         return rc;
     };
+    if (!pow2) {
+        // Bluestein: m = power of two >= 2n - 1
+        f->blue = true;
+        f->logn = 0;
+        int m = 1;
+        while (m < 2 * fft_size - 1) m <<= 1;
+        f->m = m;
+        if (window_len) {
+            f->has_window = true;
+            if (f->d_win.reserve(sizeof(float) * fft_size) != CLB200_OK) return fail(CLB200_ENOMEM);
+            if (cudaMemcpy(f->d_win.p, window, sizeof(float) * fft_size, cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("clFFT: window upload failed");
+                return fail(CLB200_ECUDA);
+            }
+        }
+        // chirp in double with the phase reduced exactly: n^2 mod 2N
+        std::vector<float2> w(fft_size);
+        std::vector<double> bre(m, 0.0), bim(m, 0.0);
+        for (int i = 0; i < fft_size; i++) {
+            const long q = ((long)i * i) % (2L * fft_size);
+            const double a = -M_PI * (double)q / (double)fft_size;
+            w[i] = make_float2((float)cos(a), (float)sin(a));
+            bre[i] = cos(a);
+            bim[i] = -sin(a);                    // conj(w)
+            if (i) {
+                bre[m - i] = bre[i];
+                bim[m - i] = bim[i];
+            }
+        }
+        // spectrum of b by a double-precision radix-2 FFT on the host (once per plan), scaled by 1/m
+        {
+            int lg = 0;
+            while ((1 << lg) < m) lg++;
+            for (int i = 0; i < m; i++) {
+                int r = 0;
+                for (int b = 0; b < lg; b++)
+                    if (i & (1 << b)) r |= 1 << (lg - 1 - b);
+                if (r > i) {
+                    std::swap(bre[i], bre[r]);
+                    std::swap(bim[i], bim[r]);
+                }
+            }
+            for (int len = 2; len <= m; len <<= 1) {
+                const int half = len >> 1;
+                for (int k = 0; k < half; k++) {
+                    const double a = -2.0 * M_PI * (double)k / (double)len, wr = cos(a), wi = sin(a);
+                    for (int i = k; i < m; i += len) {
+                        const int j = i + half;
+                        const double tr = bre[j] * wr - bim[j] * wi, ti = bre[j] * wi + bim[j] * wr;
+                        bre[j] = bre[i] - tr;
+                        bim[j] = bim[i] - ti;
+                        bre[i] += tr;
+                        bim[i] += ti;
+                    }
+                }
+            }
+        }
+        std::vector<float2> bs(m);
+        for (int i = 0; i < m; i++) bs[i] = make_float2((float)(bre[i] / m), (float)(bim[i] / m));
+        if (f->d_chirp.reserve(sizeof(float2) * fft_size) != CLB200_OK || f->d_bspec.reserve(sizeof(float2) * m) != CLB200_OK)
+            return fail(CLB200_ENOMEM);
+        if (cudaMemcpy(f->d_chirp.p, w.data(), sizeof(float2) * fft_size, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(f->d_bspec.p, bs.data(), sizeof(float2) * m, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("clFFT: chirp upload failed");
+            return fail(CLB200_ECUDA);
+        }
+        int rc = clb200_fft_create(m, CLB200_FFT_FORWARD, nullptr, 0, CLB200_DTYPE_COMPLEX, device, 0, &f->sub1);
+        if (rc == CLB200_OK) rc = clb200_fft_create(m, CLB200_FFT_BACKWARD, nullptr, 0, CLB200_DTYPE_COMPLEX, device, 0, &f->sub2);
+        if (rc != CLB200_OK) return fail(rc);
+        f->set_info("clFFT %d-pt %s: not a power of two -> chirp-z (Bluestein) over %d-point plans, window / half swaps fused "
+                    "into the pre- and post-multiply", fft_size, dir < 0 ? "forward" : "backward", m);
+        *out = f;
+        return CLB200_OK;
+    }
     if (fft_size > 16384) {
         // four-step path: two plans of the in-SM kernels (n1 >= n2, both <= 16384 up to 2^28) + transposes
         f->big = true;

@@ -153,8 +153,11 @@ CLB200_API int clb200_magphase2c_work(clb200_handle h, const float *mag, const f
  * Unnormalised in both directions (:121-122).  shift: forward swaps the output
  * halves (:594-607), backward swaps the input halves (:548-553); complex data only --
  * with dtype FLOAT the flag is ignored like the reference does (:594).
- * fft_size: power of two, 2 .. 4194304 (up to 16384 one in-SM kernel; above that a four-step
- * decomposition: two passes of those kernels around three transposes).             */
+ * fft_size: powers of two 2 .. 4194304 (up to 16384 one in-SM kernel; above that a four-step
+ * decomposition: two passes of those kernels around three transposes); any other length
+ * 2 .. 2097152 (clFFT plans take 2^a 3^b 5^c 7^d, :97-100) runs as a chirp-z (Bluestein)
+ * transform over the power-of-two kernels.  With an odd length the half swaps leave the
+ * last element in place (vlen_2 = fft_size / 2, :81).                                 */
 CLB200_API int clb200_fft_create(int fft_size, int dir, const float *window, int window_len,
                                  int dtype, int device, int shift, clb200_handle *out);
 /* processOpenCL (lib/clFFT_impl.cc:526-634): nvec items (vectors) of one stream   */

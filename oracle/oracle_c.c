@@ -400,6 +400,35 @@ static void fft_exec(const orc_fft_plan *p, const float *in, float *out, int sig
     fft_exec_bitrev(p, out, sign);
 }
 
+/* Sizes that are not a power of two (clFFT plans accept 2^a 3^b 5^c 7^d, lib/clFFT_impl.cc:97-100): the transform is
+ * the DFT definition itself, X[k] = sum_n x[n] e^{sign 2 pi i n k / N}, accumulated in double -- O(N^2), test sizes only. */
+static void dft_direct(const float *in, float *out, int n, int sign)
+{
+    double *cs = (double *)malloc(sizeof(double) * 2 * n);
+    for (int i = 0; i < n; i++) {
+        double a = sign * 2.0 * M_PI * (double)i / (double)n;
+        cs[2 * i] = cos(a);
+        cs[2 * i + 1] = sin(a);
+    }
+    for (int k = 0; k < n; k++) {
+        double re = 0, im = 0;
+        for (int i = 0; i < n; i++) {
+            int idx = (int)(((long)i * k) % n);
+            re += in[2 * i] * cs[2 * idx] - in[2 * i + 1] * cs[2 * idx + 1];
+            im += in[2 * i] * cs[2 * idx + 1] + in[2 * i + 1] * cs[2 * idx];
+        }
+        out[2 * k] = (float)re;
+        out[2 * k + 1] = (float)im;
+    }
+    free(cs);
+}
+
+static void fft_any(const orc_fft_plan *p, const float *in, float *out, int n, int sign)
+{
+    if (p) fft_exec(p, in, out, sign);
+    else dft_direct(in, out, n, sign);
+}
+
 /*
  * clFFT_impl::processOpenCL (lib/clFFT_impl.cc:526-634), complex input.
  *  dir: -1 forward (CLFFT_FORWARD, e^{-i..}), +1 backward; scale 1.0 both ways (:121-122)
@@ -410,10 +439,10 @@ static void fft_exec(const orc_fft_plan *p, const float *in, float *out, int sig
 ORC_API int orc_fft_c32(const float *in, float *out, int n, long nvec, int dir,
                         const float *window, int shift)
 {
-    orc_fft_plan *p = fft_plan_cached(n);
-    if (!p) return -1;
+    orc_fft_plan *p = fft_plan_cached(n);      /* NULL: not a power of two -> direct DFT */
+    if (n < 1) return -1;
     int fwd = (dir < 0);
-    int h = n / 2;
+    int h = n / 2;                             /* vlen_2 (:81): an odd size leaves its last element where it is */
 #pragma omp parallel
     {
         float *a = (float *)malloc(sizeof(float) * 2 * n);
@@ -422,9 +451,8 @@ ORC_API int orc_fft_c32(const float *in, float *out, int n, long nvec, int dir,
         for (long v = 0; v < nvec; v++) {
             const float *x = in + 2 * (size_t)n * v;
             float *y = out + 2 * (size_t)n * v;
-            if (fwd || !shift) {
-                memcpy(a, x, sizeof(float) * 2 * n);
-            } else {
+            memcpy(a, x, sizeof(float) * 2 * n);
+            if (!fwd && shift) {
                 memcpy(a, x + 2 * h, sizeof(float) * 2 * h);
                 memcpy(a + 2 * h, x, sizeof(float) * 2 * h);
             }
@@ -434,12 +462,11 @@ ORC_API int orc_fft_c32(const float *in, float *out, int n, long nvec, int dir,
                     a[2 * i + 1] *= window[i];
                 }
             }
-            fft_exec(p, a, c, fwd ? -1 : +1);
+            fft_any(p, a, c, n, fwd ? -1 : +1);
+            memcpy(y, c, sizeof(float) * 2 * n);
             if (fwd && shift) {
                 memcpy(y, c + 2 * h, sizeof(float) * 2 * h);
                 memcpy(y + 2 * h, c, sizeof(float) * 2 * h);
-            } else {
-                memcpy(y, c, sizeof(float) * 2 * n);
             }
         }
         free(a);
@@ -457,14 +484,14 @@ ORC_API int orc_fft_c32(const float *in, float *out, int n, long nvec, int dir,
 ORC_API int orc_fft_r32(const float *in, float *out, int n, long nvec, const float *window)
 {
     orc_fft_plan *p = fft_plan_cached(n);
-    if (!p) return -1;
+    if (n < 1) return -1;
     float *a = (float *)malloc(sizeof(float) * 2 * n);
     for (long v = 0; v < nvec; v++) {
         for (int i = 0; i < n; i++) {
             a[2 * i] = in[(size_t)n * v + i] * (window ? window[i] : 1.0f);
             a[2 * i + 1] = 0.0f;
         }
-        fft_exec(p, a, out + 2 * (size_t)n * v, -1);
+        fft_any(p, a, out + 2 * (size_t)n * v, n, -1);
     }
     free(a);
     return 0;

@@ -118,7 +118,8 @@ def test_empty_calls_and_bad_arguments_for_every_block():
         assert f.work(e).size == 0
         assert f.work(np.ones(1, c64)).size == 1 and f.work(np.ones(1, c64)).size == 0     # decimation phase carried
     assert blocks.clQuadratureDemod(1.0, *GPU).work(e).size == 0
-    for bad in (lambda: blocks.clFFT(1000, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU),            # not a power of two
+    for bad in (lambda: blocks.clFFT(1, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU),
+                lambda: blocks.clFFT((1 << 21) + 2, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU),  # non-power-of-two limit
                 lambda: blocks.clFFT(1024, capi.FFT_FORWARD, np.ones(100, np.float32), capi.DTYPE_COMPLEX, *GPU),
                 lambda: blocks.clFFT(1024, 0, [], capi.DTYPE_COMPLEX, *GPU),
                 lambda: blocks.clFFT(1024, capi.FFT_BACKWARD, [], capi.DTYPE_FLOAT, *GPU),             # real input is forward-only
@@ -205,6 +206,30 @@ def test_fft_real_input_and_streams():
     outs = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU, 0, 3).work_streams(xs)
     for xi, oi in zip(xs, outs):
         assert rel_err(oi, orc.fft(xi, N, -1)) < TOL
+
+
+@pytest.mark.parametrize("N", [3, 5, 6, 7, 12, 100, 243, 1000, 1001, 1200, 3125, 4095, 10000, 20000])
+def test_fft_sizes_that_are_not_a_power_of_two(N):
+    """clFFT plans take any 2^a 3^b 5^c 7^d length (lib/clFFT_impl.cc:97-100); here every length runs as a chirp-z
+    transform over the power-of-two kernels: all window / shift / direction / real-input combinations against the oracle
+    (direct DFT in double) and pocketfft, plus the round trip"""
+    nvec = 5 if N <= 4095 else 2
+    x = orc.rng_c32(N * nvec, orc.SEED_F + 30)
+    w = orc.window_blackman(N)
+    ref = np.fft.fft(x.astype(np.complex128).reshape(nvec, N), axis=1).reshape(-1)
+    got = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU).work(x)
+    assert rel_err(got, ref) < 3e-6
+    assert rel_err(got, orc.fft(x, N, -1)) < TOL
+    if N <= 4095:
+        for direction in (capi.FFT_FORWARD, capi.FFT_BACKWARD):
+            for win in (None, w):
+                for shift in (False, True):
+                    blk = blocks.clFFT(N, direction, [] if win is None else win, capi.DTYPE_COMPLEX, *GPU, 0, 1, shift)
+                    assert rel_err(blk.work(x), orc.fft(x, N, direction, win, shift)) < TOL, (direction, win is None, shift)
+        xr = orc.rng_f32(N * nvec, orc.SEED_F + 31)
+        assert rel_err(blocks.clFFT(N, capi.FFT_FORWARD, w, capi.DTYPE_FLOAT, *GPU, 0, 1, True).work(xr), orc.fft_real(xr, N, w)) < TOL
+    back = blocks.clFFT(N, capi.FFT_BACKWARD, [], capi.DTYPE_COMPLEX, *GPU).work(got) / N
+    assert rel_err(back, x) < TOL
 
 
 @pytest.mark.parametrize("N", [32768, 65536, 1 << 18, 1 << 20])

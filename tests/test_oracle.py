@@ -405,3 +405,26 @@ def test_unpack4_lut():
     out = orc.unpack4(b).reshape(256, 2)
     lut = np.array([0, 1, 2, 3, 4, 5, 6, 7, 0, -7, -6, -5, -4, -3, -2, -1])   # clXEngine_impl.cc:833
     assert np.array_equal(out[:, 0], lut[b >> 4]) and np.array_equal(out[:, 1], lut[b & 15])
+
+
+@pytest.mark.parametrize("n", [3, 12, 100, 243, 1001])
+def test_fft_oracle_any_length_matches_pocketfft(n):
+    """lengths that are not a power of two take the direct DFT (double accumulation); the half swaps use
+    vlen_2 = n / 2 (lib/clFFT_impl.cc:81): an odd length leaves its last element in place"""
+    x = orc.rng_c32(n * 3, orc.SEED_F + 40)
+    xx = x.reshape(3, n).astype(np.complex128)
+    h = n // 2
+    for direction in (-1, 1):
+        for shift in (False, True):
+            a = xx.copy()
+            if direction > 0 and shift:
+                a[:, :h], a[:, h:2 * h] = xx[:, h:2 * h], xx[:, :h]
+            ref = np.fft.fft(a, axis=1) if direction < 0 else np.fft.ifft(a, axis=1) * n
+            if direction < 0 and shift:
+                r = ref.copy()
+                ref[:, :h], ref[:, h:2 * h] = r[:, h:2 * h], r[:, :h]
+            got = orc.fft(x, n, direction, None, shift).reshape(3, n)
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-6
+    xr = orc.rng_f32(n * 2, orc.SEED_F + 41)
+    ref = np.fft.fft(xr.reshape(2, n).astype(np.float64), axis=1)
+    assert np.max(np.abs(orc.fft_real(xr, n).reshape(2, n) - ref)) / np.max(np.abs(ref)) < 1e-6
