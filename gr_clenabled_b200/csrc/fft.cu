@@ -384,6 +384,11 @@ const FftVariant *pick_variant(int logn)
     return &tab[logn - 1];
 }
 
+struct ColVariant;
+const ColVariant *pick_col(int logn);
+struct Fft;
+int fft_setup_two_pass(Fft *f, const ColVariant *ca, const ColVariant *cb);
+
 struct Fft : clb200_block {
     int n = 0, logn = 0, dir = 0, dtype = 0, shift = 0, mode = 0;
     bool has_window = false;
@@ -396,6 +401,11 @@ struct Fft : clb200_block {
     int loop_form = 1;     // which of the two work-counter loop forms (kernel_d / kernel_u)
     // sizes above 16384 (one CTA's shared memory): N = n1 x n2, two passes of the in-SM kernels around transposes
     bool big = false;
+    // 32768 .. 1048576 points: two passes of column transforms (k_fft_col) instead of the five of the four-step path
+    bool two_pass = false;
+    const ColVariant *colA = nullptr, *colB = nullptr;
+    Buf d_twA, d_twB, d_tw4;     // twiddles of the two column plans; W_N^j (j < 512) followed by W_N^(512 j) (j < N / 512)
+    int col_resident[2] = {1, 1};
     // sizes that are not a power of two: chirp-z (Bluestein) on top of two power-of-two plans of m >= 2n-1 points
     bool blue = false;
     int m = 0;
@@ -413,6 +423,9 @@ struct Fft : clb200_block {
         d_win.release();
         d_chirp.release();
         d_bspec.release();
+        d_twA.release();
+        d_twB.release();
+        d_tw4.release();
         for (auto &sc : scratch) {
             sc.a.release();
             sc.b.release();
@@ -481,6 +494,118 @@ __global__ void __launch_bounds__(256) k_fft_tr(const void *__restrict__ in, flo
 }
 
 int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st);
+Fft::Scratch *fft_scratch(Fft *f, cudaStream_t st, size_t bytes, int *rc);
+
+// ---- 32768 .. 1048576 points in TWO passes over HBM: column transforms ------------------------------------------
+// The four-step decomposition above spends three of its five passes on transposes.  Here a CTA owns C = 16 adjacent
+// COLUMNS of the [NA][NB] view of a vector (128 B runs of every row, CTAs that run together take neighbouring runs of
+// the same rows), thread = (column, element group) with the column fastest so that the global accesses coalesce; each
+// column has its own shared-memory line of ODD length (16 columns x the same element = 16 distinct bank pairs).
+//   pass A: x as [N1][N2], columns n2: window / backward half swap / real input fused into the load, N1-point
+//           transforms, then through shared memory once more so that the store runs along k1:
+//           T'[n2][k1] = W_N^(n2 k1) X_n2[k1]  (full rows, coalesced);
+//   pass B: T' as [N2][N1], columns k1: N2-point transforms, stored straight from registers to X[k2 N1 + k1]
+//           (forward half swap fused).
+// The backward transform is the forward one on re/im-swapped data (swapped by pass A's load and pass B's store).
+template <int LOGN, int EPT, int C, int MINB, int PASSB>
+__global__ void __launch_bounds__((1 << LOGN) / EPT * C, MINB)
+k_fft_col(const void *__restrict__ in, float2 *__restrict__ out, long nvec, int nb, int n, const float2 *__restrict__ tw,
+          const float *__restrict__ win, int xor_idx, int real_in, int inverse, const float2 *__restrict__ tw4)
+{
+    using P = Plan<LOGN, EPT>;
+    constexpr int NA = P::N, T = P::T, LINE = P::SMEM_F2 | 1;
+    extern __shared__ __align__(16) float2 smem[];
+    const int tb = threadIdx.x % C, lt = threadIdx.x / C;
+    float2 *buf = smem + tb * LINE;
+    const int groups = nb / C;
+    const long ntile = nvec * groups;
+    for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long v = tile / groups;
+        const int c0 = (int)(tile - v * groups) * C;
+        const long base = v * (long)n;
+        float2 x[EPT];
+        static_for<0, EPT>([&](auto e_) {
+            constexpr int e = decltype(e_)::value;
+            const int idx = in_index<P, EPT>(lt, e) * nb + c0 + tb;
+            float2 a;
+            if (PASSB) {
+                a = reinterpret_cast<const float2 *>(in)[base + idx];
+            } else {
+                const int src = idx ^ xor_idx;                         // backward + shift: input halves swapped
+                a = real_in ? make_float2(reinterpret_cast<const float *>(in)[base + src], 0.f)
+                            : reinterpret_cast<const float2 *>(in)[base + src];
+                if (win != nullptr) {
+                    const float w = __ldg(win + idx);
+                    a.x *= w;
+                    a.y *= w;
+                }
+                if (inverse) a = make_float2(a.y, a.x);
+            }
+            x[e] = a;
+        });
+        fft_core<P, EPT, NoHook, 1, false>(x, buf, lt, tw);
+        if (PASSB) {
+            for_each_output<P, EPT>(x, lt, [&](int k, float2 a) {
+                const int o = (k * nb + c0 + tb) ^ xor_idx;           // forward + shift: output halves swapped
+                if (inverse) a = make_float2(a.y, a.x);
+                __stcs(out + base + o, a);
+            });
+        } else {
+            __syncthreads();                                           // the last pass has read its inputs
+            for_each_output<P, EPT>(x, lt, [&](int k, float2 a) { buf[P::pad(k)] = a; });
+            __syncthreads();
+            for (int i = threadIdx.x; i < C * NA; i += T * C) {
+                const int col = i >> LOGN, k = i & (NA - 1);
+                float2 a = smem[col * LINE + P::pad(k)];
+                // W_N^(n2 k1) = W_N^(512 hi) * W_N^lo: two L1-resident tables of <= 512 entries, one rounding
+                const unsigned ph = ((unsigned)(c0 + col) * (unsigned)k) & (unsigned)(n - 1);
+                a = cmul(a, cmul(__ldg(tw4 + 512 + (ph >> 9)), __ldg(tw4 + (ph & 511))));
+                __stcs(out + base + (long)(c0 + col) * NA + k, a);
+            }
+        }
+    }
+}
+
+typedef void (*fft_col_kernel_t)(const void *, float2 *, long, int, int, const float2 *, const float *, int, int, int, const float2 *);
+struct ColVariant {
+    int logn, threads, smem_bytes;
+    void (*fill_tw)(std::vector<float2> &);
+    fft_col_kernel_t kernel[2];      // pass A, pass B
+};
+template <int LOGN, int EPT, int MINB>
+ColVariant make_col()
+{
+    using P = Plan<LOGN, EPT>;
+    return ColVariant{LOGN, P::T * 16, (P::SMEM_F2 | 1) * 16 * (int)sizeof(float2), &fill_tw_t<LOGN, EPT>,
+                      {&k_fft_col<LOGN, EPT, 16, MINB, 0>, &k_fft_col<LOGN, EPT, 16, MINB, 1>}};
+}
+
+const ColVariant *pick_col(int logn)
+{
+    static const ColVariant c7 = make_col<7, 16, 6>(), c8 = make_col<8, 16, 3>(), c9 = make_col<9, 32, 2>(),
+                            c10 = make_col<10, 32, 1>();
+    return logn == 7 ? &c7 : logn == 8 ? &c8 : logn == 9 ? &c9 : logn == 10 ? &c10 : nullptr;
+}
+
+int fft_launch_two_pass(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
+{
+    int rc = CLB200_OK;
+    Fft::Scratch *sc = fft_scratch(f, st, (size_t)nvec * f->n * sizeof(float2), &rc);
+    if (!sc) return rc;
+    float2 *t = (float2 *)sc->a.p;
+    const int N1 = f->n1, N2 = f->n2, half = f->n >> 1, sms = device_sm_count(f->device);
+    const int inverse = f->dir > 0;
+    const long tilesA = nvec * (N2 / 16), tilesB = nvec * (N1 / 16);
+    f->colA->kernel[0]<<<grid_for(tilesA, sms, f->col_resident[0]), f->colA->threads, f->colA->smem_bytes, st>>>(
+        d_in, t, nvec, N2, f->n, (const float2 *)f->d_twA.p, f->has_window ? (const float *)f->d_win.p : nullptr,
+        (f->shift && inverse) ? half : 0, f->dtype == CLB200_DTYPE_FLOAT, inverse, (const float2 *)f->d_tw4.p);
+    f->colB->kernel[1]<<<grid_for(tilesB, sms, f->col_resident[1]), f->colB->threads, f->colB->smem_bytes, st>>>(
+        t, (float2 *)d_out, nvec, N1, f->n, (const float2 *)f->d_twB.p, nullptr, (f->shift && !inverse) ? half : 0, 0, inverse,
+        nullptr);
+    CLB_CUDA(cudaGetLastError());
+    f->n_launch += 2;
+    return CLB200_OK;
+}
 
 // ---- sizes that are not a power of two: Bluestein ------------------------------------------------------------
 // clFFT plans accept any 2^a 3^b 5^c 7^d length (lib/clFFT_impl.cc:97-100 hands fftSize straight to
@@ -539,8 +664,6 @@ __global__ void __launch_bounds__(256) k_blue_post(const float2 *__restrict__ c,
         out[v * n + (swap_h ? blue_swap(k, swap_h) : k)] = val;
     }
 }
-
-Fft::Scratch *fft_scratch(Fft *f, cudaStream_t st, size_t bytes, int *rc);
 
 int fft_launch_blue(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
 {
@@ -615,6 +738,7 @@ int fft_launch(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st
 {
     if (nvec <= 0) return CLB200_OK;
     if (f->blue) return fft_launch_blue(f, d_in, d_out, nvec, st);
+    if (f->two_pass) return fft_launch_two_pass(f, d_in, d_out, nvec, st);
     if (f->big) return fft_launch_big(f, d_in, d_out, nvec, st);
     const FftVariant *v = f->var;
     long ntile = (nvec + v->batch - 1) / v->batch;
@@ -690,6 +814,44 @@ int xcfft_launch(XcFft *x, const void *const *d_in, void *const *d_out, long nve
         x->n_launch++;
     }
     CLB_CUDA(cudaGetLastError());
+    return CLB200_OK;
+}
+
+int fft_setup_two_pass(Fft *f, const ColVariant *ca, const ColVariant *cb)
+{
+    const ColVariant *cv[2] = {ca, cb};
+    Buf *tw[2] = {&f->d_twA, &f->d_twB};
+    for (int p = 0; p < 2; p++) {
+        std::vector<float2> t;
+        cv[p]->fill_tw(t);
+        CLB_TRY(tw[p]->reserve(t.size() * sizeof(float2)));
+        CLB_CUDA(cudaMemcpy(tw[p]->p, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        const void *k = (const void *)cv[p]->kernel[p];
+        int occ = 0;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, cv[p]->smem_bytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, cv[p]->threads, cv[p]->smem_bytes) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            return CLB200_OK;                  // does not fit: the caller falls back to the four-step path
+        }
+        f->col_resident[p] = occ;
+    }
+    {
+        const int nhi = std::max(1, f->n / 512);
+        std::vector<float2> t(512 + nhi, make_float2(1.f, 0.f));
+        for (int j = 0; j < 512; j++) {
+            const double a = -2.0 * M_PI * (double)j / (double)f->n;
+            t[j] = make_float2((float)cos(a), (float)sin(a));
+        }
+        for (int j = 0; j < nhi; j++) {
+            const double b = -2.0 * M_PI * (512.0 * j) / (double)f->n;
+            t[512 + j] = make_float2((float)cos(b), (float)sin(b));
+        }
+        CLB_TRY(f->d_tw4.reserve(t.size() * sizeof(float2)));
+        CLB_CUDA(cudaMemcpy(f->d_tw4.p, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    f->colA = ca;
+    f->colB = cb;
+    f->two_pass = true;
     return CLB200_OK;
 }
 
@@ -908,6 +1070,21 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
             if (cudaMemcpy(f->d_win.p, window, sizeof(float) * fft_size, cudaMemcpyHostToDevice) != cudaSuccess) {
                 set_error("clFFT: window upload failed");
                 return fail(CLB200_ECUDA);
+            }
+        }
+        {
+            const char *e = getenv("CLB200_FFT_FOURSTEP");          // A/B: force the five-pass path
+            const ColVariant *ca = pick_col(ilog2(f->n1)), *cb = pick_col(ilog2(f->n2));
+            if (!(e && atoi(e)) && ca && cb) {
+                int rc2 = fft_setup_two_pass(f, ca, cb);
+                if (rc2 != CLB200_OK) return fail(rc2);
+                if (f->two_pass) {
+                    f->set_info("clFFT %d-pt %s: two passes over HBM: %d-point column transforms (window / swaps / twiddles fused, "
+                                "stored along k1) and %d-point column transforms, 16 columns per CTA", fft_size,
+                                dir < 0 ? "forward" : "backward", f->n1, f->n2);
+                    *out = f;
+                    return CLB200_OK;
+                }
             }
         }
         int rc = clb200_fft_create(f->n1, dir, nullptr, 0, CLB200_DTYPE_COMPLEX, device, 0, &f->sub1);

@@ -304,7 +304,8 @@ struct NoHook {
 // entries are the same for every transform a thread runs, and reading them with LDS keeps them out of the
 // global-load queue (the 8192-point kernel stalls on lg_throttle: 59 twiddle LDGs per 32 data LDGs).
 // TWD: twiddle derivation mode (see CLB_TW_DERIVE)
-template <class P, int EPT, class Hook = NoHook, int TWD = CLB_TW_DERIVE>
+// V128 = false: no 128-bit shared-memory stores (lines that are only 8 B aligned: the column transforms of fft.cu)
+template <class P, int EPT, class Hook = NoHook, int TWD = CLB_TW_DERIVE, bool V128 = true>
 __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
                                          const float2 *__restrict__ tw, Hook after_last_load = Hook{},
                                          const float2 *tw1s = nullptr)
@@ -376,7 +377,7 @@ __device__ __forceinline__ void fft_core(float2 (&x)[EPT], float2 *buf, int lt,
 
         if constexpr (!last) {
             if constexpr (first) __syncthreads();
-            if constexpr (NS == 1 && (R % 2 == 0)) {
+            if constexpr (V128 && NS == 1 && (R % 2 == 0)) {
                 // thread-contiguous run of R outputs: 128-bit stores
                 float2 *const sp = buf + P::pad(lt * R);
                 static_for<0, NB>([&](auto u_) {

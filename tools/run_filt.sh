@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "fft or FFT or zero or bad or ctor or argument" 2>&1 | tail -8
+timeout 300 python -m pytest tests -m gpu -x -q -k "above_16384 or not_a_power" 2>&1 | tail -4
+timeout 300 python tools/fft_big_ab.py 2>&1 | head -6
