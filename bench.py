@@ -341,6 +341,16 @@ def secondary_blocks(torch, blocks, capi, dev, stream_ptr, hbm_peak):
         out["clPolyphaseChannelizer_64ch"] = hbm(16 * niter * M, t, niter * M)
     except Exception as e:                           # noqa: BLE001
         out["clPolyphaseChannelizer_64ch"] = {"error": str(e)}
+    try:
+        # clFFT outside the one-kernel sizes: 65536 points (two passes of column transforms) and 10000 points (not a
+        # power of two: chirp-z over 32768-point plans); 16 B/sample algorithmic like the headline
+        for name, N in (("clFFT_65536pt_two_pass", 65536), ("clFFT_10000pt_chirpz", 10000)):
+            nv = (1 << 24) // N if N == 10000 else n // N
+            blk = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *gpu)
+            t = _timeit(torch, lambda: blk.launch_device(a.data_ptr(), b.data_ptr(), nv, stream_ptr), 3)
+            out[name] = hbm(16 * nv * N, t, nv * N)
+    except Exception as e:                           # noqa: BLE001
+        out["clFFT_other_sizes"] = {"error": str(e)}
     del a, b
     try:
         A, F, T, K = 32, 1024, 1024, 16

@@ -60,6 +60,9 @@ for rep, dst, key, alg in (("fft.ncu-rep", "fft8192_full.txt", "k_fft_8192pt_x81
                            ("fftfilt.ncu-rep", "fftfilt_full.txt", "k_fftfilt_256tap_64Mi", 1073741824),
                            ("fir.ncu-rep", "fir_full.txt", "k_fir_256tap_64Mi", 1073741824),
                            ("pfb.ncu-rep", "pfb_full.txt", "k_pfb_64ch_64Mi", 1073741824),
+                           ("map1.ncu-rep", "mathconst_full.txt", "k_map1_multiplyconst_64Mi", 1073741824),
+                           ("fftcolA.ncu-rep", "fft65536_passA_full.txt", "k_fft_col_passA_65536pt_x1024vec", 1073741824),
+                           ("fftcolB.ncu-rep", "fft65536_passB_full.txt", "k_fft_col_passB_65536pt_x1024vec", 1073741824),
                            ("xe_tma.ncu-rep", "xengine_full.txt", "k_xengine_tma_32st_1024ch_1024t", XE),
                            ("xe_batch.ncu-rep", "xengine_batch16_full.txt", "k_xengine_tma_batch16_32st_1024ch_1024t", 16 * XE),
                            ("xe_c32.ncu-rep", "xengine_c32_full.txt", "k_xengine_c32_32st_256ch_1024t", 32 * 256 * 1024 * 8 + 256 * 528 * 8),

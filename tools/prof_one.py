@@ -1,4 +1,4 @@
-"""Launches one block's device-resident kernel a few times (for ncu).  usage: prof_one.py fft|xengine|xengine_batch|xengine_c32|filter|pfb|fir [variant]"""
+"""Launches one block's device-resident kernel a few times (for ncu).  usage: prof_one.py fft|fft65536|mathconst|xengine|xengine_batch|xengine_c32|filter|pfb|fir [variant]"""
 import os
 import sys
 
@@ -21,6 +21,20 @@ if what == "fft":
     f = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *gpu)
     for _ in range(reps):
         f.launch_device(x.data_ptr(), y.data_ptr(), nvec, sp)
+elif what == "fft65536":
+    N, nvec = 65536, 1024
+    x = torch.empty(N * nvec * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
+    y = torch.empty_like(x)
+    f = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *gpu)
+    for _ in range(reps):
+        f.launch_device(x.data_ptr(), y.data_ptr(), nvec, sp)
+elif what == "mathconst":
+    n = 1 << 26
+    x = torch.empty(n * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
+    y = torch.empty_like(x)
+    blk = blocks.clMathConst(capi.DTYPE_COMPLEX, *gpu, 0.7071, capi.OP_MULTIPLY)
+    for _ in range(reps):
+        blk.launch_device(x.data_ptr(), y.data_ptr(), n, sp)
 elif what == "xengine":
     A, F, T = 32, 1024, 1024
     npol = int(sys.argv[2]) if len(sys.argv) > 2 else 1
