@@ -32,6 +32,32 @@ struct OpSub  { __device__ static float f(float a, float k) { return __fsub_rn(a
 __device__ __forceinline__ float4 ld4(const float4 *p) { return __ldcs(p); }
 __device__ __forceinline__ void st4(float4 *p, float4 v) { __stcs(p, v); }
 
+// Tile loop shared by the element-wise kernels: `nv` vector items in tiles of EW_THREADS x U, handed out by the work
+// counter (common.cuh: tile_fetch; static striding when wq is null).  full(i) handles the U items i + u * EW_THREADS
+// of a whole tile (all loads first), one(i) a single item of the ragged end (first CTA).
+template <int U, class Full, class One>
+__device__ __forceinline__ void ew_tile_loop(long nv, unsigned long long *wq, Full &&full, One &&one)
+{
+    constexpr long TILE = (long)EW_THREADS * U;
+    __shared__ long s_next[2];                 // double-buffered: a slow reader of tile t never sees the index written for t + 1
+    const long ntile = nv / TILE;
+    int it = 0;
+    for (long tile = blockIdx.x; tile < ntile; it ^= 1) {
+        long nxt = tile + gridDim.x;
+        if (wq != nullptr && threadIdx.x == 0) nxt = tile_fetch(wq);
+        full(tile * TILE + threadIdx.x);
+        if (wq != nullptr) {
+            if (threadIdx.x == 0) s_next[it] = nxt;
+            __syncthreads();
+            nxt = s_next[it];
+        }
+        tile = nxt;
+    }
+    if (wq != nullptr && threadIdx.x == 0) tile_finish(wq);
+    if (blockIdx.x == 0)
+        for (long i = ntile * TILE + threadIdx.x; i < nv; i += EW_THREADS) one(i);
+}
+
 // ---- 1 in -> 1 out over float4 vectors ------------------------------------
 // Tiles of EW_THREADS x EW_UNROLL vectors (16 KiB) handed out by the work counter (common.cuh: tile_fetch; static
 // striding without one): the resident CTAs of an SM then all stay busy until the launch ends.
@@ -167,28 +193,19 @@ __global__ void __launch_bounds__(EW_THREADS)
 k_map2(const float4 *__restrict__ a, const float4 *__restrict__ b, float4 *__restrict__ c,
        long nvec, Bin f, unsigned long long *wq)
 {
-    constexpr long TILE = (long)EW_THREADS * 2;           // two vectors per operand in flight per thread (8 KiB per operand)
-    __shared__ long s_next[2];
-    const long ntile = nvec / TILE;
-    int it = 0;
-    for (long tile = blockIdx.x; tile < ntile; it ^= 1) {
-        long nxt = tile + gridDim.x;
-        if (wq != nullptr && threadIdx.x == 0) nxt = tile_fetch(wq);
-        const long i = tile * TILE + threadIdx.x;
-        float4 a0 = ld4(a + i), a1 = ld4(a + i + EW_THREADS);
-        float4 b0 = ld4(b + i), b1 = ld4(b + i + EW_THREADS);
-        st4(c + i, f.vec(a0, b0));
-        st4(c + i + EW_THREADS, f.vec(a1, b1));
-        if (wq != nullptr) {
-            if (threadIdx.x == 0) s_next[it] = nxt;
-            __syncthreads();
-            nxt = s_next[it];
-        }
-        tile = nxt;
-    }
-    if (wq != nullptr && threadIdx.x == 0) tile_finish(wq);
-    if (blockIdx.x == 0)
-        for (long i = ntile * TILE + threadIdx.x; i < nvec; i += EW_THREADS) st4(c + i, f.vec(ld4(a + i), ld4(b + i)));
+    constexpr int U = 2;                                  // two vectors per operand in flight per thread
+    ew_tile_loop<U>(nvec, wq,
+        [&](long i) {
+            float4 va[U], vb[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                va[u] = ld4(a + i + u * EW_THREADS);
+                vb[u] = ld4(b + i + u * EW_THREADS);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) st4(c + i + u * EW_THREADS, f.vec(va[u], vb[u]));
+        },
+        [&](long i) { st4(c + i, f.vec(ld4(a + i), ld4(b + i))); });
 }
 
 // element granularity fallback / tail: `pairs` = process float2 items (complex) else floats
@@ -233,24 +250,27 @@ int launch_map2(const void *a, const void *b, void *c, long nfloats, Bin f, int 
 
 // ---- secondary kernels (item granularity; transcendental -> not bit-exact) ----
 __global__ void __launch_bounds__(EW_THREADS)
-k_log10(const float *__restrict__ a, float *__restrict__ c, long n, float factor, float k)
+k_log10(const float *__restrict__ a, float *__restrict__ c, long n, float factor, float k, unsigned long long *wq)
 {   // c = (n/log2(10)) * log2(a) + k    (clLog_impl.cc:139-148)
-    long stride = (long)gridDim.x * EW_THREADS;
     const bool vec = (((uintptr_t)a | (uintptr_t)c) & 15) == 0;
-    const long nv = vec ? n / 4 : 0;                       // 16 B per access, two in flight per thread
-    long i = (long)blockIdx.x * EW_THREADS + threadIdx.x;
-    for (; i + stride < nv; i += 2 * stride) {
-        const float4 v0 = ld4(reinterpret_cast<const float4 *>(a) + i), v1 = ld4(reinterpret_cast<const float4 *>(a) + i + stride);
-        st4(reinterpret_cast<float4 *>(c) + i, make_float4(fmaf(factor, log2f(v0.x), k), fmaf(factor, log2f(v0.y), k),
-                                                            fmaf(factor, log2f(v0.z), k), fmaf(factor, log2f(v0.w), k)));
-        st4(reinterpret_cast<float4 *>(c) + i + stride, make_float4(fmaf(factor, log2f(v1.x), k), fmaf(factor, log2f(v1.y), k),
-                                                                     fmaf(factor, log2f(v1.z), k), fmaf(factor, log2f(v1.w), k)));
-    }
-    for (; i < nv; i += stride) {
-        const float4 v = ld4(reinterpret_cast<const float4 *>(a) + i);
-        st4(reinterpret_cast<float4 *>(c) + i, make_float4(fmaf(factor, log2f(v.x), k), fmaf(factor, log2f(v.y), k),
-                                                            fmaf(factor, log2f(v.z), k), fmaf(factor, log2f(v.w), k)));
-    }
+    const long nv = vec ? n / 4 : 0;                       // 16 B per access, four in flight per thread
+    const float4 *a4 = reinterpret_cast<const float4 *>(a);
+    float4 *c4 = reinterpret_cast<float4 *>(c);
+    auto f4 = [&](float4 v) {
+        return make_float4(fmaf(factor, log2f(v.x), k), fmaf(factor, log2f(v.y), k), fmaf(factor, log2f(v.z), k),
+                           fmaf(factor, log2f(v.w), k));
+    };
+    constexpr int U = 4;
+    ew_tile_loop<U>(nv, wq,
+        [&](long i) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = ld4(a4 + i + u * EW_THREADS);
+#pragma unroll
+            for (int u = 0; u < U; u++) st4(c4 + i + u * EW_THREADS, f4(v[u]));
+        },
+        [&](long i) { st4(c4 + i, f4(ld4(a4 + i))); });
+    const long stride = (long)gridDim.x * EW_THREADS;
     for (long j = nv * 4 + (long)blockIdx.x * EW_THREADS + threadIdx.x; j < n; j += stride)
         c[j] = fmaf(factor, log2f(a[j]), k);
 }
@@ -266,29 +286,27 @@ k_snr(const float *__restrict__ a, const float *__restrict__ b, float *__restric
 
 template <bool MAG, bool ARG>
 __global__ void __launch_bounds__(EW_THREADS)
-k_c2mp(const float2 *__restrict__ a, float *__restrict__ mag, float *__restrict__ ph, long n)
+k_c2mp(const float2 *__restrict__ a, float *__restrict__ mag, float *__restrict__ ph, long n, unsigned long long *wq)
 {   // complextomag / complextoarg / complextomagphase
-    long stride = (long)gridDim.x * EW_THREADS;
     // two samples per access (16 B in, 8 B out per output stream) when the pointers allow it
     const bool vec = (((uintptr_t)a & 15) | ((MAG ? (uintptr_t)mag : 0) & 7) | ((ARG ? (uintptr_t)ph : 0) & 7)) == 0;
     const long nv = vec ? n / 2 : 0;
-    long i = (long)blockIdx.x * EW_THREADS + threadIdx.x;
-    for (; i + stride < nv; i += 2 * stride) {
-        const float4 v0 = ld4(reinterpret_cast<const float4 *>(a) + i), v1 = ld4(reinterpret_cast<const float4 *>(a) + i + stride);
-        if (MAG) {
-            __stcs(reinterpret_cast<float2 *>(mag) + i, make_float2(sqrtf(v0.y * v0.y + v0.x * v0.x), sqrtf(v0.w * v0.w + v0.z * v0.z)));
-            __stcs(reinterpret_cast<float2 *>(mag) + i + stride, make_float2(sqrtf(v1.y * v1.y + v1.x * v1.x), sqrtf(v1.w * v1.w + v1.z * v1.z)));
-        }
-        if (ARG) {
-            __stcs(reinterpret_cast<float2 *>(ph) + i, make_float2(atan2f(v0.y, v0.x), atan2f(v0.w, v0.z)));
-            __stcs(reinterpret_cast<float2 *>(ph) + i + stride, make_float2(atan2f(v1.y, v1.x), atan2f(v1.w, v1.z)));
-        }
-    }
-    for (; i < nv; i += stride) {
-        const float4 v = ld4(reinterpret_cast<const float4 *>(a) + i);
+    const float4 *a4 = reinterpret_cast<const float4 *>(a);
+    auto put = [&](long i, float4 v) {
         if (MAG) __stcs(reinterpret_cast<float2 *>(mag) + i, make_float2(sqrtf(v.y * v.y + v.x * v.x), sqrtf(v.w * v.w + v.z * v.z)));
         if (ARG) __stcs(reinterpret_cast<float2 *>(ph) + i, make_float2(atan2f(v.y, v.x), atan2f(v.w, v.z)));
-    }
+    };
+    constexpr int U = 4;
+    ew_tile_loop<U>(nv, wq,
+        [&](long i) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = ld4(a4 + i + u * EW_THREADS);
+#pragma unroll
+            for (int u = 0; u < U; u++) put(i + u * EW_THREADS, v[u]);
+        },
+        [&](long i) { put(i, ld4(a4 + i)); });
+    const long stride = (long)gridDim.x * EW_THREADS;
     for (long j = nv * 2 + (long)blockIdx.x * EW_THREADS + threadIdx.x; j < n; j += stride) {
         float2 v = __ldcs(a + j);
         if (MAG) mag[j] = sqrtf(v.y * v.y + v.x * v.x);
@@ -311,6 +329,15 @@ k_mp2c(const float *__restrict__ mag, const float *__restrict__ ph, float2 *__re
 inline int item_grid(long n, int sms)
 {
     return grid_for((n + EW_THREADS - 1) / EW_THREADS, sms, EW_CTAS_PER_SM);
+}
+// grid and work counter of the tiled kernels (tiles of EW_THREADS x 4 vector items)
+inline int tile_grid(long nv, int sms)
+{
+    return grid_for((nv + EW_THREADS * 4 - 1) / (EW_THREADS * 4), sms, EW_CTAS_PER_SM);
+}
+inline unsigned long long *tile_wq(clb200_block *b, long nv, int sms, cudaStream_t st)
+{
+    return nv / (EW_THREADS * 4) > 2L * sms * EW_CTAS_PER_SM ? b->work_counter(st) : nullptr;
 }
 
 // ---------------------------------------------------------------- handles ----
@@ -499,17 +526,17 @@ static int unary_launch(Unary *u, const void *in, void *out, long n, cudaStream_
     u->n_launch++;
     switch (u->ukind) {
     case CLB200_UNARY_LOG10:
-        k_log10<<<item_grid(n, sms), EW_THREADS, 0, st>>>((const float *)in, (float *)out, n,
-                                                           (float)((double)u->nv / 3.321928094887362),
-                                                           u->kv);
+        k_log10<<<tile_grid(n / 4, sms), EW_THREADS, 0, st>>>((const float *)in, (float *)out, n,
+                                                               (float)((double)u->nv / 3.321928094887362),
+                                                               u->kv, tile_wq(u, n / 4, sms, st));
         break;
     case CLB200_UNARY_COMPLEX_TO_MAG:
-        k_c2mp<true, false><<<item_grid(n, sms), EW_THREADS, 0, st>>>((const float2 *)in, (float *)out,
-                                                                     nullptr, n);
+        k_c2mp<true, false><<<tile_grid(n / 2, sms), EW_THREADS, 0, st>>>((const float2 *)in, (float *)out,
+                                                                         nullptr, n, tile_wq(u, n / 2, sms, st));
         break;
     case CLB200_UNARY_COMPLEX_TO_ARG:
-        k_c2mp<false, true><<<item_grid(n, sms), EW_THREADS, 0, st>>>((const float2 *)in, nullptr,
-                                                                     (float *)out, n);
+        k_c2mp<false, true><<<tile_grid(n / 2, sms), EW_THREADS, 0, st>>>((const float2 *)in, nullptr,
+                                                                         (float *)out, n, tile_wq(u, n / 2, sms, st));
         break;
     }
     CLB_CUDA(cudaGetLastError());
@@ -631,8 +658,8 @@ int clb200_c2magphase_work(clb200_handle h, const void *in, float *mag, float *p
     return run_chunked(u, pd, nitems, chunk_for(pd),
                        [&](const void **di, void **dout, long n, cudaStream_t st, long *) {
                            u->n_launch++;
-                           k_c2mp<true, true><<<item_grid(n, sms), EW_THREADS, 0, st>>>(
-                               (const float2 *)di[0], (float *)dout[0], (float *)dout[1], n);
+                           k_c2mp<true, true><<<tile_grid(n / 2, sms), EW_THREADS, 0, st>>>(
+                               (const float2 *)di[0], (float *)dout[0], (float *)dout[1], n, tile_wq(u, n / 2, sms, st));
                            CLB_CUDA(cudaGetLastError());
                            return CLB200_OK;
                        });

@@ -1,3 +1,2 @@
-cap() { REPS=3 timeout 300 ncu --set full --clock-control none --import-source on -k "regex:$1" -s ${4:-1} -c 1 -f -o gpurun_out/$2 python tools/prof_one.py $3 > gpurun_out/ncu_$2.log 2>&1; echo "$2 rc=$?"; }
-cap "^k_fft$" fft fft
-ls -la gpurun_out/
+for s in 0 1; do echo "== STATIC=$s"; CLB200_STATIC_TILES=$s timeout 300 python tools/time_blocks.py 2>&1 | grep -E "^(clMultiply|clComplex|clLog)" | cut -c1-200; done
+timeout 600 python -m pytest tests -m gpu -x -q -k "mathconst or mathop or log or snr or mag or arg or unary or secondary or dynamic or zero" 2>&1 | tail -3
