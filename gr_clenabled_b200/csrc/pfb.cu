@@ -128,13 +128,118 @@ k_pfb(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
     }
 }
 
+// Critically sampled (R == M) with NT <= 4 taps per arm: the sample an arm multiplies by tap group g at time step i is
+// the one it multiplies by group 0 at step i - g.  A thread group therefore walks PFB_RUN CONSECUTIVE time steps and
+// keeps the last NT - 1 steps' samples in registers: every input sample is loaded once instead of NT times (the
+// kernel is LSU-bound: L1 data-pipe wavefronts 91 % busy in profiles/r2_pfb_full.txt); the next step's samples are in
+// flight while a step's transform runs.  Used where it measured faster (clb200_pfb_create).  Tiles (BATCH x PFB_RUN
+// steps) come from the work counter when the CTA is a single warp (common.cuh: tile_fetch), else by static striding.
+constexpr int PFB_RUN = 16;
+template <int LOGM, int EPT, int BATCH, int MINB, int NT>
+__global__ void __launch_bounds__((1 << LOGM) / EPT * BATCH, MINB)
+k_pfb_run(const float2 *__restrict__ in, float2 *__restrict__ out, long niter,
+          const float *__restrict__ taps, const float2 *__restrict__ tw, const int *__restrict__ map,
+          int ntaps, int nmap, int identity, unsigned long long *wq)
+{
+    using P = Plan<LOGM, EPT>;
+    constexpr int M = P::N, T = P::T;
+    constexpr int LINE = (P::SMEM_F2 > P::pad(M)) ? P::SMEM_F2 : P::pad(M);
+    constexpr bool one_warp = T * BATCH == 32;
+    extern __shared__ __align__(16) float2 smem[];
+    const int tb = (BATCH == 1) ? 0 : threadIdx.x / T;
+    const int lt = (BATCH == 1) ? threadIdx.x : threadIdx.x % T;
+    float2 *buf = smem + tb * LINE;
+    float tr[NT][EPT];
+    bool ok[NT][EPT];
+#pragma unroll
+    for (int g = 0; g < NT; g++)
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const int k = g * M + in_index<P, EPT>(lt, e);
+            ok[g][e] = k < ntaps;
+            tr[g][e] = ok[g][e] ? __ldg(taps + k) : 0.f;
+        }
+    // sample of arm slot e at time step i: in[i*M + ntaps-1 - j[e]]
+    const float2 *const base = in + (ntaps - 1) - lt;
+    const long ntile = (niter + (long)BATCH * PFB_RUN - 1) / ((long)BATCH * PFB_RUN);
+    for (long tile = blockIdx.x; tile < ntile;) {
+        long nxt = tile + gridDim.x;
+        if (one_warp && wq != nullptr && threadIdx.x == 0) nxt = tile_fetch(wq);
+        const long i0 = (tile * BATCH + tb) * PFB_RUN;
+        float2 w[NT][EPT];
+        // the NT - 1 steps in front of the run (history samples precede the first step)
+#pragma unroll
+        for (int g = 1; g < NT; g++)
+#pragma unroll
+            for (int e = 0; e < EPT; e++)
+                w[g][e] = (ok[g][e] && i0 < niter) ? __ldg(base + (i0 - g) * (long)M - (in_index<P, EPT>(0, e)))
+                                                   : make_float2(0.f, 0.f);
+        // the next step's samples are in flight while this step's transform runs
+        float2 nx[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+            nx[e] = (ok[0][e] && i0 < niter) ? __ldg(base + i0 * (long)M - (in_index<P, EPT>(0, e))) : make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int s = 0; s < PFB_RUN; s++) {
+            const long i = i0 + s;
+            const bool active = i < niter;
+            float2 x[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; e++) w[0][e] = nx[e];
+            {
+                const bool more = s + 1 < PFB_RUN && i + 1 < niter;
+#pragma unroll
+                for (int e = 0; e < EPT; e++)
+                    nx[e] = (ok[0][e] && more) ? __ldg(base + (i + 1) * (long)M - (in_index<P, EPT>(0, e))) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; e++) x[e] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int g = 0; g < NT; g++)
+#pragma unroll
+                for (int e = 0; e < EPT; e++) {      // ascending k like the reference (:163); x holds (im, re): inverse via the forward core
+                    x[e].y = fmaf(w[g][e].x, tr[g][e], x[e].y);
+                    x[e].x = fmaf(w[g][e].y, tr[g][e], x[e].x);
+                }
+#pragma unroll
+            for (int g = NT - 1; g >= 1; g--)
+#pragma unroll
+                for (int e = 0; e < EPT; e++) w[g][e] = w[g - 1][e];
+
+            fft_core<P, EPT>(x, buf, lt, tw);
+
+            if (identity) {
+                if (active) {
+                    float2 *dst = out + i * (long)M;
+                    for_each_output<P, EPT>(x, lt, [&](int o, float2 a) { __stcs(dst + o, make_float2(a.y, a.x)); });
+                }
+            } else {
+                __syncthreads();        // the last pass' reads of buf are done
+                for_each_output<P, EPT>(x, lt, [&](int o, float2 a) { buf[P::pad(o)] = make_float2(a.y, a.x); });
+                __syncthreads();
+                if (active) {
+                    float2 *dst = out + i * (long)nmap;
+                    for (int q = lt; q < nmap; q += T) dst[q] = buf[P::pad(__ldg(map + q))];
+                }
+                __syncthreads();        // before the next time step overwrites buf
+            }
+        }
+        if (one_warp && wq != nullptr) nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        tile = nxt;
+    }
+    if (one_warp && wq != nullptr && threadIdx.x == 0) tile_finish(wq);
+}
+
 typedef void (*pfb_kernel_t)(const float2 *, float2 *, long, const float *, const float2 *,
                              const int *, int, int, int, int);
+typedef void (*pfb_run_kernel_t)(const float2 *, float2 *, long, const float *, const float2 *,
+                                 const int *, int, int, int, unsigned long long *);
 struct PfbVariant {
     int logm, batch, threads, smem_bytes;
     void (*fill_tw)(std::vector<float2> &);
     pfb_kernel_t kernel;          // any R, any tap count
     pfb_kernel_t kernel_crit[2];  // R == M and <= 2 / <= 4 taps per arm: taps in registers
+    pfb_run_kernel_t kernel_run[2];   // the same with runs of consecutive time steps per thread group (samples loaded once)
 };
 
 template <int LOGM, int EPT>
@@ -159,7 +264,8 @@ PfbVariant make_pfb()
     constexpr int LINE = (P::SMEM_F2 > P::pad(P::N)) ? P::SMEM_F2 : P::pad(P::N);
     return PfbVariant{LOGM, BATCH, P::T * BATCH, LINE * BATCH * (int)sizeof(float2),
                       &fill_tw_p<LOGM, EPT>, &k_pfb<LOGM, EPT, BATCH, MINB, 0>,
-                      {&k_pfb<LOGM, EPT, BATCH, MINB, 2>, &k_pfb<LOGM, EPT, BATCH, MINB, 4>}};
+                      {&k_pfb<LOGM, EPT, BATCH, MINB, 2>, &k_pfb<LOGM, EPT, BATCH, MINB, 4>},
+                      {&k_pfb_run<LOGM, EPT, BATCH, (MINB > 16 ? 16 : MINB), 2>, &k_pfb_run<LOGM, EPT, BATCH, (MINB > 16 ? 16 : MINB), 4>}};
 }
 
 const PfbVariant *pick_pfb(int logm)
@@ -180,6 +286,7 @@ struct Pfb : clb200_block {
     int ntaps = 0, M = 0, R = 0, nmap = 0, buf_items = 0, identity = 0, resident = 1;
     const PfbVariant *var = nullptr;
     pfb_kernel_t kernel = nullptr;
+    pfb_run_kernel_t kernel_run = nullptr;   // set: the run kernel replaces `kernel`
     Buf d_taps, d_tw, d_map;
     ~Pfb() override
     {
@@ -194,6 +301,18 @@ int pfb_launch(Pfb *p, const void *d_in, void *d_out, long niter, cudaStream_t s
 {
     if (niter <= 0) return CLB200_OK;
     const PfbVariant *v = p->var;
+    if (p->kernel_run) {
+        const long per = (long)v->batch * PFB_RUN;
+        const long ntile = (niter + per - 1) / per;
+        const int grid = grid_for(ntile, device_sm_count(p->device), p->resident);
+        p->kernel_run<<<grid, v->threads, v->smem_bytes, st>>>(
+            (const float2 *)d_in, (float2 *)d_out, niter, (const float *)p->d_taps.p, (const float2 *)p->d_tw.p,
+            (const int *)p->d_map.p, p->ntaps, p->nmap, p->identity,
+            (v->threads == 32 && ntile > grid) ? p->work_counter(st) : nullptr);
+        CLB_CUDA(cudaGetLastError());
+        p->n_launch++;
+        return CLB200_OK;
+    }
     long ntile = (niter + v->batch - 1) / v->batch;
     int grid = grid_for(ntile, device_sm_count(p->device), p->resident);
     p->kernel<<<grid, v->threads, v->smem_bytes, st>>>(
@@ -262,15 +381,23 @@ int clb200_pfb_create(int device, const float *taps, int ntaps, int buf_items, i
     {
         const char *gen = getenv("CLB200_PFB_GENERAL");           // A/B: force the general kernel
         const int per_arm = (ntaps + M - 1) / M;
-        if (R == M && per_arm <= 4 && !(gen && atoi(gen))) p->kernel = p->var->kernel_crit[per_arm <= 2 ? 0 : 1];
+        if (R == M && per_arm <= 4 && !(gen && atoi(gen))) {
+            p->kernel = p->var->kernel_crit[per_arm <= 2 ? 0 : 1];
+            // runs of consecutive time steps: measured (tools/pfb_ab.py) +12 % at 64 channels x 4 taps per arm and +47 % at
+            // 16 x 4, but -7 % at 64 x 2 (the BASELINE shape: the second read of a sample is an L1 hit there and the run's
+            // serial steps cost more than it saves) and -14 ... -18 % with multi-warp CTAs: one-warp CTAs with 3-4 taps per arm
+            const char *run = getenv("CLB200_PFB_RUN");           // A/B: 0 = never, 1 = whenever the kernel exists
+            const bool want = run ? atoi(run) != 0 : (p->var->threads == 32 && per_arm > 2);
+            if (want) p->kernel_run = p->var->kernel_run[per_arm <= 2 ? 0 : 1];
+        }
     }
-    cudaError_t e = cudaFuncSetAttribute((const void *)p->kernel,
+    const void *kfn = p->kernel_run ? (const void *)p->kernel_run : (const void *)p->kernel;
+    cudaError_t e = cudaFuncSetAttribute(kfn,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          p->var->smem_bytes);
     int occ = 0;
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)p->kernel,
-                                                          p->var->threads, p->var->smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, p->var->threads, p->var->smem_bytes);
     if (e != cudaSuccess || occ < 1) {
         set_error("clPolyphaseChannelizer: kernel does not fit an SM (%s)", cudaGetErrorString(e));
         return fail(CLB200_ECUDA);

@@ -423,6 +423,7 @@ def test_filter_full_size_linearity(golden):
 @pytest.mark.parametrize("M,R,T,cmap", [
     (64, 64, 128, None), (64, 32, 128, None), (64, 64, 127, [5, 0, 63, 5]), (8, 8, 24, [3, 0, 5]),
     (2, 2, 7, None), (16, 4, 50, None), (256, 256, 1024, None), (1024, 512, 2048, [0, 1023, 7]),
+    (64, 64, 256, None), (16, 16, 64, None), (64, 64, 200, [1, 2, 63]), (32, 32, 97, None),     # 3-4 taps per arm: the run kernel
 ])
 def test_pfb_vs_oracle(M, R, T, cmap):
     taps = (orc.rng_f32(T, orc.SEED_P) * 0.1).astype(np.float32)
@@ -432,6 +433,21 @@ def test_pfb_vs_oracle(M, R, T, cmap):
     blk = blocks.clPolyphaseChannelizer(*GPU, taps, M * 4, M, R, cmap)
     got = blk.work(x, niter)
     assert rel_err(got, orc.pfb(x, taps, M, R, cmap, niter)) < TOL
+
+
+@pytest.mark.parametrize("M,T", [(64, 128), (64, 256), (8, 16), (256, 512), (1024, 4096)])
+def test_pfb_runs_of_time_steps_equal_single_steps(M, T, monkeypatch):
+    """critically sampled, <= 4 taps per arm: a thread group walking consecutive time steps with the earlier samples in
+    registers (k_pfb_run) gives the bits of the one-step-per-tile kernel, whichever of the two the block would pick"""
+    taps = (orc.rng_f32(T, orc.SEED_P + 5) * 0.1).astype(np.float32)
+    niter = 1000 if M <= 64 else 77
+    x = orc.rng_c32((niter - 1) * M + T, orc.SEED_P + 6)
+    outs = []
+    for run in ("0", "1"):
+        monkeypatch.setenv("CLB200_PFB_RUN", run)
+        outs.append(blocks.clPolyphaseChannelizer(*GPU, taps, M * 4, M, M, list(range(M))).work(x, niter))
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert rel_err(outs[1], orc.pfb(x, taps, M, M, list(range(M)), niter)) < TOL
 
 
 def test_pfb_baseline_config_tone_and_scale(golden):
