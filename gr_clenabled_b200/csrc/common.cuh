@@ -105,6 +105,7 @@ struct clb200_block {
     clb200::Buf work_ctr_buf;
     cudaStream_t work_ctr_stream[WORK_CTRS] = {};
     int work_ctr_used = 0;
+    bool init_work_counters();
     unsigned long long *work_counter(cudaStream_t st);
 };
 

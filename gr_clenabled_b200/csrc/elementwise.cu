@@ -408,6 +408,7 @@ int clb200_mathconst_create(int dtype, int device, float k, int op, clb200_handl
     MathConst *m = new MathConst;
     m->kind = KIND_MATHCONST;
     m->device = device;
+    m->init_work_counters();
     m->dtype = dtype;
     m->op = op;
     m->k = k;
@@ -476,6 +477,7 @@ int clb200_mathop_create(int dtype, int device, int op, clb200_handle *out)
     MathOp *m = new MathOp;
     m->kind = KIND_MATHOP;
     m->device = device;
+    m->init_work_counters();
     m->dtype = dtype;
     m->op = op;
     *out = m;
@@ -554,6 +556,7 @@ int clb200_unary_create(int kind, int device, float n_value, float k_value, clb2
     Unary *u = new Unary;
     u->kind = KIND_UNARY;
     u->device = device;
+    u->init_work_counters();
     u->ukind = kind;
     u->nv = n_value;
     u->kv = k_value;

@@ -974,6 +974,7 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
     Fft *f = new Fft;
     f->kind = KIND_FFT;
     f->device = device;
+    f->init_work_counters();
     f->n = fft_size;
     f->logn = ilog2(fft_size);
     f->dir = dir;

@@ -832,6 +832,7 @@ int clb200_filter_create(int device, int decimation, const float *taps, int ntap
     Filter *f = new Filter;
     f->kind = KIND_FILTER;
     f->device = device;
+    f->init_work_counters();
     f->decim = decimation;
     f->use_time = use_time ? 1 : 0;
     int rc = filter_configure(f, std::vector<float>(taps, taps + ntaps));

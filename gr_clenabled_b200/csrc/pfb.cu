@@ -354,6 +354,7 @@ int clb200_pfb_create(int device, const float *taps, int ntaps, int buf_items, i
     Pfb *p = new Pfb;
     p->kind = KIND_PFB;
     p->device = device;
+    p->init_work_counters();
     p->ntaps = ntaps;
     p->M = M;
     p->R = R;

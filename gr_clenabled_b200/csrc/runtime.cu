@@ -136,18 +136,26 @@ int clb200_block::init_slots()
     return CLB200_OK;
 }
 
+// the records are allocated and zeroed when the handle is created (a cudaMemset at launch time would synchronise
+// with the caller's streams, and is not allowed while one of them is being captured into a graph)
+bool clb200_block::init_work_counters()
+{
+    if (work_ctr_buf.p) return true;
+    DeviceGuard g(device);
+    if (work_ctr_buf.reserve(16 * WORK_CTRS) != CLB200_OK) return false;
+    if (cudaMemset(work_ctr_buf.p, 0, 16 * WORK_CTRS) != cudaSuccess) {
+        cudaGetLastError();
+        work_ctr_buf.release();
+        return false;
+    }
+    return true;
+}
+
 unsigned long long *clb200_block::work_counter(cudaStream_t st)
 {
     const char *e = getenv("CLB200_STATIC_TILES");      // A/B switch, read per launch
     if (e && atoi(e) != 0) return nullptr;
-    if (!work_ctr_buf.p) {
-        if (work_ctr_buf.reserve(16 * WORK_CTRS) != CLB200_OK) return nullptr;
-        if (cudaMemset(work_ctr_buf.p, 0, 16 * WORK_CTRS) != cudaSuccess) {
-            cudaGetLastError();
-            work_ctr_buf.release();
-            return nullptr;
-        }
-    }
+    if (!work_ctr_buf.p && !init_work_counters()) return nullptr;
     int i = 0;
     for (; i < work_ctr_used; i++)
         if (work_ctr_stream[i] == st) break;

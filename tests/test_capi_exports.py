@@ -48,8 +48,9 @@ def test_argument_checks_before_device_use():
     w = (C.c_float * 4)()
     rc = lib.clb200_fft_create(8, -1, C.cast(w, C.c_void_p), 4, capi.DTYPE_COMPLEX, 0, 0, C.byref(h))
     assert rc == capi.EINVAL and "window not the same length" in capi.last_error()
-    rc = lib.clb200_fft_create(100, -1, None, 0, capi.DTYPE_COMPLEX, 0, 0, C.byref(h))
-    assert rc == capi.EINVAL
+    for bad_size in (1, (1 << 22) + 1, 1 << 23):      # any length 2 .. 2 Mi, powers of two to 4 Mi
+        rc = lib.clb200_fft_create(bad_size, -1, None, 0, capi.DTYPE_COMPLEX, 0, 0, C.byref(h))
+        assert rc == capi.EINVAL and "fft size" in capi.last_error()
     # clXEngine ctor: at least 2 inputs (lib/clXEngine_impl.cc:106-109)
     rc = lib.clb200_xengine_create(0, capi.DTYPE_BYTE, 1, 1, 16, 16, C.byref(h))
     assert rc == capi.EINVAL and "at least 2 inputs" in capi.last_error()
