@@ -408,16 +408,23 @@ __host__ __device__ constexpr int fir_pad(int i) { return i + (i >> 3); }
 
 // decimation 1: register sliding window, taps (reversed, zero-padded to K8) and
 // the input tile in shared memory
+// PK: the (re, im) pair of an output is accumulated by ONE packed fma (fma.rn.f32x2 -> FFMA2; the tap sits in both
+// halves of a register pair, read as {t, t} from shared memory): 64 instead of 128 fma instructions per step, same bits.
+template <bool PK>
 __global__ void __launch_bounds__(FIR_THREADS)
 k_fir_d1(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_in,
          float2 *__restrict__ out, const float *__restrict__ rtaps, int K, int K8, unsigned long long *wq)
 {
     __shared__ long s_next;
     extern __shared__ __align__(16) unsigned char fir_smem[];
-    float *s_t = reinterpret_cast<float *>(fir_smem);                     // K8 floats
-    float2 *s_x = reinterpret_cast<float2 *>(fir_smem + (size_t)K8 * 4);  // fir_pad(TILE + K8)
+    float *s_t = reinterpret_cast<float *>(fir_smem);                     // K8 floats (PK: K8 pairs {t, t})
+    float2 *s_t2 = reinterpret_cast<float2 *>(fir_smem);
+    float2 *s_x = reinterpret_cast<float2 *>(fir_smem + (size_t)K8 * (PK ? 8 : 4));  // fir_pad(TILE + K8)
     const int km1 = K - 1;
-    for (int i = threadIdx.x; i < K8; i += FIR_THREADS) s_t[i] = rtaps[i];
+    for (int i = threadIdx.x; i < K8; i += FIR_THREADS) {
+        if (PK) s_t2[i] = make_float2(rtaps[i], rtaps[i]);
+        else s_t[i] = rtaps[i];
+    }
     const long ntile = (n_in + FIR_TILE - 1) / FIR_TILE;
     for (long tile = blockIdx.x; tile < ntile;) {
         long nxt = tile + gridDim.x;                      // tiles from the work counter (common.cuh) when there is one
@@ -443,16 +450,30 @@ k_fir_d1(const float2 *__restrict__ hist, const float2 *__restrict__ in, long n_
             wp += FIR_OPT + 1;
 #pragma unroll
             for (int j = 0; j < FIR_OPT; j++) w[FIR_OPT + j] = wp[j];
-            const float4 t0 = *reinterpret_cast<const float4 *>(s_t + i);
-            const float4 t1 = *reinterpret_cast<const float4 *>(s_t + i + 4);
-            const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            if constexpr (PK) {
+                float2 tt[FIR_OPT];
 #pragma unroll
-            for (int ii = 0; ii < FIR_OPT; ii++)
-#pragma unroll
-                for (int j = 0; j < FIR_OPT; j++) {
-                    acc[j].x = fmaf(t[ii], w[ii + j].x, acc[j].x);
-                    acc[j].y = fmaf(t[ii], w[ii + j].y, acc[j].y);
+                for (int q = 0; q < FIR_OPT / 2; q++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(s_t2 + i + 2 * q);
+                    tt[2 * q] = make_float2(t.x, t.y);
+                    tt[2 * q + 1] = make_float2(t.z, t.w);
                 }
+#pragma unroll
+                for (int ii = 0; ii < FIR_OPT; ii++)
+#pragma unroll
+                    for (int j = 0; j < FIR_OPT; j++) acc[j] = cfma_real(tt[ii], w[ii + j], acc[j]);
+            } else {
+                const float4 t0 = *reinterpret_cast<const float4 *>(s_t + i);
+                const float4 t1 = *reinterpret_cast<const float4 *>(s_t + i + 4);
+                const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                for (int ii = 0; ii < FIR_OPT; ii++)
+#pragma unroll
+                    for (int j = 0; j < FIR_OPT; j++) {
+                        acc[j].x = fmaf(t[ii], w[ii + j].x, acc[j].x);
+                        acc[j].y = fmaf(t[ii], w[ii + j].y, acc[j].y);
+                    }
+            }
 #pragma unroll
             for (int j = 0; j < FIR_OPT; j++) w[j] = w[FIR_OPT + j];
         }
@@ -582,6 +603,7 @@ struct Filter : clb200_block {
     int skip = 0;                       // decimation phase: inputs to drop before the next output
     int k8 = 0;
     int resident = 1;
+    bool fir_packed = true;             // time-domain kernel with packed fma (k_fir_d1<true>)
     int pf = 0, resident_pf = 1;        // prefetching one-warp kernel (0: off, 1: L2, 2: shared memory) and its occupancy
     int compact = 0, resident_c = 1, smem_c = 0;   // compact one-warp kernel k_fftfilt_1w (1: plain loads, 2: bulk-copy prefetch)
     cudaEvent_t hist_ready = nullptr;
@@ -629,16 +651,22 @@ int filter_configure(Filter *f, const std::vector<float> &taps)
         for (int i = 0; i < K; i++) rt[i] = taps[K - 1 - i];      // FilterArray[K-1-i] (:187)
         CLB_TRY(f->d_rtaps.reserve(sizeof(float) * f->k8));
         CLB_CUDA(cudaMemcpy(f->d_rtaps.p, rt.data(), sizeof(float) * f->k8, cudaMemcpyHostToDevice));
-        size_t smem = (size_t)f->k8 * 4 + sizeof(float2) * fir_pad(FIR_TILE + f->k8 + 8);
+        {
+            const char *pk = getenv("CLB200_FIR_PACKED");         // A/B
+            f->fir_packed = pk ? atoi(pk) != 0 : true;
+        }
+        size_t smem = (size_t)f->k8 * (f->fir_packed ? 8 : 4) + sizeof(float2) * fir_pad(FIR_TILE + f->k8 + 8);
         CLB_CHECK(smem <= 200 * 1024, CLB200_EINVAL, "clFilter: %d taps exceed the FIR kernel's shared memory", K);
         // the limit is per-function state shared by every clFilter handle of the process: always the cap the
         // kernels may need, never the size of the filter configured last
-        CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_d1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_d1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_d1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CLB_CUDA(cudaFuncSetAttribute((const void *)k_fir_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         // as many resident CTAs as fit (5 at 256 taps): one CTA's tile load and barriers hide behind the
         // others' FMA loops -- 32.2 (2 CTAs/SM) -> 38.0 Gsamples/s at 256 taps
         int occ = 0;
-        CLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_fir_d1, FIR_THREADS, smem));
+        CLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, f->fir_packed ? (const void *)k_fir_d1<true> : (const void *)k_fir_d1<false>, FIR_THREADS, smem));
         f->resident = std::max(1, std::min(occ, 8));
         if (fir_ctas_per_sm() > 0) f->resident = fir_ctas_per_sm();
     } else {
@@ -743,8 +771,8 @@ int filter_launch(Filter *f, const float2 *d_in, long n_in, float2 *d_out, long 
         if (f->time_kernel) {
             if (D == 1) {
                 long ntile = (n_in + FIR_TILE - 1) / FIR_TILE;
-                size_t smem = (size_t)f->k8 * 4 + sizeof(float2) * fir_pad(FIR_TILE + f->k8 + 8);
-                k_fir_d1<<<grid_for(ntile, sms, f->resident), FIR_THREADS, smem, st>>>(
+                size_t smem = (size_t)f->k8 * (f->fir_packed ? 8 : 4) + sizeof(float2) * fir_pad(FIR_TILE + f->k8 + 8);
+                (f->fir_packed ? k_fir_d1<true> : k_fir_d1<false>)<<<grid_for(ntile, sms, f->resident), FIR_THREADS, smem, st>>>(
                     hist, d_in, n_in, d_out, (const float *)f->d_rtaps.p, K, f->k8,
                     ntile > (long)sms * f->resident ? f->work_counter(st) : nullptr);
             } else {
