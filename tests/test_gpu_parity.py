@@ -232,6 +232,22 @@ def test_fft_sizes_that_are_not_a_power_of_two(N):
     assert rel_err(back, x) < TOL
 
 
+@pytest.mark.parametrize("N,nvec", [(65536, 90), (1000, 6500), (1 << 21, 3)])
+def test_fft_multi_kernel_sizes_through_the_chunked_host_path(N, nvec):
+    """the sizes that need scratch buffers (two-pass, chirp-z, five-pass), with enough vectors for several 32 MiB chunks
+    on the three slot streams: every chunk owns its scratch, vectors sampled across all chunks against the oracle"""
+    x = orc.rng_c32(N * nvec, orc.SEED_F + 50)
+    blk = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *GPU, 0, 1, True)
+    got = blk.work(x)
+    got2 = blk.work(x)                                   # scratch reused by the second call
+    assert np.array_equal(got.view(np.uint32), got2.view(np.uint32))
+    pick = sorted(set([0, nvec - 1] + list(range(0, nvec, max(1, nvec // 12)))))
+    xs = np.concatenate([x[v * N:(v + 1) * N] for v in pick]).astype(np.complex128).reshape(len(pick), N)
+    ref = np.fft.fftshift(np.fft.fft(xs, axis=1), axes=1) if N % 2 == 0 else None
+    gs = np.concatenate([got[v * N:(v + 1) * N] for v in pick]).reshape(len(pick), N)
+    assert rel_err(gs, ref) < 3e-6
+
+
 @pytest.mark.parametrize("N", [32768, 65536, 1 << 18, 1 << 20])
 def test_fft_sizes_above_16384_four_step(N):
     """sizes beyond one CTA's shared memory (clFFT plans accept them: waterfalls of 32768 / 65536 points): four-step
