@@ -357,8 +357,8 @@ FftVariant make_variant()
     return v;
 }
 
-// default instantiation per size; alternates selectable with CLB200_FFT_VARIANT
-// (used by the tuning script).  {LOGN, EPT, transforms per CTA, min CTAs/SM}
+// one instantiation per size, {LOGN, EPT, transforms per CTA, min CTAs/SM}.  (The 8192-point alternates the rounds
+// measured -- 16 or 8 elements per thread, one CTA per SM: 2.9-4.0 TB/s, DESIGN.md 4.1 -- are no longer compiled in.)
 const FftVariant *pick_variant(int logn)
 {
     static const FftVariant tab[] = {
@@ -368,18 +368,6 @@ const FftVariant *pick_variant(int logn)
         make_variant<10, 16, 4, 2>(),   make_variant<11, 16, 2, 2>(),  make_variant<12, 16, 1, 2>(),
         make_variant<13, 32, 1, 2>(),   make_variant<14, 32, 1, 1>(),
     };
-    static const FftVariant alt[] = {
-        make_variant<13, 16, 1, 2>(),   // CLB200_FFT_VARIANT=1
-        make_variant<13, 32, 1, 1>(),   // 2
-        make_variant<13, 16, 1, 1>(),   // 3
-        make_variant<13, 8, 1, 1>(),    // 4
-        make_variant<13, 8, 1, 2>(),    // 5
-    };
-    if (logn == 13) {
-        const char *e = getenv("CLB200_FFT_VARIANT");
-        int a = e ? atoi(e) : 0;
-        if (a >= 1 && a <= (int)(sizeof(alt) / sizeof(alt[0]))) return &alt[a - 1];
-    }
     if (logn < 1 || logn > 14) return nullptr;
     return &tab[logn - 1];
 }

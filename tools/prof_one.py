@@ -13,8 +13,6 @@ sp = torch.cuda.current_stream().cuda_stream
 gpu = (1, 1, 0, 0)
 reps = int(os.environ.get("REPS", "3"))
 if what == "fft":
-    if len(sys.argv) > 2:
-        os.environ["CLB200_FFT_VARIANT"] = sys.argv[2]
     N, nvec = 8192, 8192
     x = torch.empty(N * nvec * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
     y = torch.empty_like(x)
