@@ -312,7 +312,7 @@ void fill_tw_t(std::vector<float2> &tw)
 // which work-counter loop form a size uses (0: static striding)
 constexpr int fft_loop_form(int logn)
 {
-    return (logn == 8 || logn == 9 || logn == 12 || logn == 13) ? 1 : logn == 14 ? 2 : 0;
+    return (logn >= 6 && logn <= 13) ? 1 : logn == 14 ? 2 : 0;
 }
 
 template <int LOGN, int EPT, int BATCH, int MINB>
@@ -334,8 +334,11 @@ FftVariant make_variant()
     v.kernel_pf[0] = v.kernel_pf[1] = nullptr;
     v.kernel_xc = &k_xcfft<LOGN, EPT, BATCH, MINB>;
     v.kernel_d[0] = v.kernel_d[1] = v.kernel_d[2] = nullptr;
-    // measured per size on B200 (tools/fft_dyn_ab.py, static striding = 100 %): form 1: 256 points 114 %, 512: 103 %,
-    // 1024: 99 %, 2048: 97 %, 4096: 107 %, 8192: 110 %, 16384: 101 %; form 2: 16384 points 105 %
+    // measured per size on B200 (tools/fft_dyn_ab.py -> profiles/r2_tile_ab.txt), round-1 instantiation with static
+    // striding = 100 %: with tiles of >= 2048 samples and the fewest passes (64: 8x8 x 32 transforms per CTA, 128: 16x8,
+    // 512: 32x16, 1024: 32x32, 2048: 32x32x2) and work-counter tiles -- 64 points 116 %, 128: 111 %, 256: 114 %, 512: 108 %,
+    // 1024: 119 %, 2048: 107 %, 4096: 107 %, 8192: 110 %, 16384: 105 % (loop form 2); 16 and 32 points keep their small
+    // static tiles (larger or dynamic ones measured slower)
     if constexpr (P::npass() > 1 && fft_loop_form(LOGN) == 1) {
         v.kernel_d[0] = &k_fft<LOGN, EPT, BATCH, MINB, 8>;
         v.kernel_d[1] = &k_fft<LOGN, EPT, BATCH, MINB, 9>;
@@ -363,9 +366,9 @@ const FftVariant *pick_variant(int logn)
 {
     static const FftVariant tab[] = {
         make_variant<1, 2, 32, 24>(),   make_variant<2, 4, 32, 24>(),  make_variant<3, 8, 32, 16>(),
-        make_variant<4, 4, 8, 24>(),    make_variant<5, 8, 8, 24>(),   make_variant<6, 8, 4, 24>(),
-        make_variant<7, 8, 2, 24>(),    make_variant<8, 16, 16, 2>(),  make_variant<9, 8, 4, 4>(),
-        make_variant<10, 16, 4, 2>(),   make_variant<11, 16, 2, 2>(),  make_variant<12, 16, 1, 2>(),
+        make_variant<4, 4, 8, 24>(),    make_variant<5, 8, 8, 24>(),   make_variant<6, 8, 32, 2>(),
+        make_variant<7, 16, 16, 4>(),   make_variant<8, 16, 16, 2>(),  make_variant<9, 32, 16, 2>(),
+        make_variant<10, 32, 8, 2>(),   make_variant<11, 32, 4, 2>(),  make_variant<12, 16, 1, 2>(),
         make_variant<13, 32, 1, 2>(),   make_variant<14, 32, 1, 1>(),
     };
     if (logn < 1 || logn > 14) return nullptr;
