@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-{ echo "clFFT size sweep, device-resident, 64 Mi samples per launch (tools/fft_sweep.py; % of the 6543.7 GB/s copy figure)"; timeout 300 python tools/fft_sweep.py; } > gpurun_out/ev_fft_sweep.txt 2>&1
-{ echo "clFFT: static striding vs work-counter tiles (columns form1 = form2 = the per-size default loop form; 16 and 32 points always stride statically), alternating in one process, GB/s (tools/fft_dyn_ab.py)"; timeout 300 python tools/fft_dyn_ab.py 4 5 6 7 8 9 10 11 12 13 14; } > gpurun_out/ev_tile_ab.txt 2>&1
-cat gpurun_out/ev_fft_sweep.txt
+mkdir -p gpurun_out
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
+timeout 600 python bench.py > gpurun_out/bench_r2c.json 2> gpurun_out/bench_r2c.err; echo "bench rc=$?"
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2c_ref.json 2>> gpurun_out/bench_r2c.err; echo "ref rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()"
