@@ -438,10 +438,11 @@ struct XeC32 {
 constexpr int C32_SLOTS = 4;    // 16 B staging loads per thread and tile (vector path)
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) k_xengine_c32_tiled(XeC32 p)
+__global__ void __launch_bounds__(256, 2) k_xengine_c32_tiled(XeC32 p)
 {
     extern __shared__ __align__(16) float2 c32_smem[];          // 2 x [C32_TT][ch][NVP]
-    const int NVP = p.NB * 4;                                   // rows padded to whole blocks
+    const int NVP = p.NB * 4 + 2;                               // rows padded to whole blocks, + 16 B: the channels of a tile
+                                                                // start on different banks (rows of 256 B collided)
     const int CH = p.ch;
     const int tid = threadIdx.x;
     const int grp = blockIdx.x, slice = blockIdx.y;
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(256) k_xengine_c32_tiled(XeC32 p)
             const float4 *row = reinterpret_cast<const float4 *>(buf + c * NVP + bi * 4);
             const float4 *col = reinterpret_cast<const float4 *>(buf + c * NVP + bj * 4);
             const int tstride = CH * NVP / 2;                   // float4 per time step
-#pragma unroll 4
+#pragma unroll 8
             for (int t = 0; t < nt; t++) {
                 const float4 r01 = row[t * tstride], r23 = row[t * tstride + 1];
                 const float4 c01 = col[t * tstride], c23 = col[t * tstride + 1];
@@ -815,7 +816,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         q.nout = x->out_items();
         CLB_CHECK(q.nblk <= 256, CLB200_EINVAL, "clXEngine: too many inputs for the complex kernel");
         // channels per CTA: one thread per (channel, 4 x 4 block), at most 256 threads and 48 KiB of staged samples
-        int ch = std::min(std::min(256 / q.nblk, 384 / (q.NB * 4)), 32);
+        int ch = std::min(std::min(256 / q.nblk, 384 / (q.NB * 4 + 2)), 32);
         if (ch >= 4) ch &= ~3;
         ch = std::max(1, std::min(ch, x->F));
         q.ch = ch;
@@ -831,7 +832,7 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         } else {
             q.out = out_f32;
         }
-        const size_t smem = 2 * (size_t)C32_TT * ch * q.NB * 4 * sizeof(float2);         // two staging buffers
+        const size_t smem = 2 * (size_t)C32_TT * ch * (q.NB * 4 + 2) * sizeof(float2);   // two staging buffers
         // 16 B staging loads: whole float4 per (t, station) run, 16 B aligned rows, few enough slots per thread
         const bool vec = (ch * x->npol) % 2 == 0 && ((long)Fstride * x->npol) % 2 == 0 && ((long)f_off * x->npol) % 2 == 0 &&
                          ((uintptr_t)d_in % 16) == 0 && (ch % 2 == 0 || x->npol == 2) &&

@@ -1,5 +1,2 @@
-mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
-timeout 600 python bench.py > gpurun_out/bench_r2c.json 2> gpurun_out/bench_r2c.err; echo "bench rc=$?"
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2c_ref.json 2>> gpurun_out/bench_r2c.err; echo "ref rc=$?"
-python -c "import __graft_entry__ as g; g.smoke()"
+timeout 300 python -m pytest tests -m gpu -x -q -k "xengine" 2>&1 | tail -2
+for i in 1 2; do timeout 300 python tools/time_blocks.py 2>&1 | grep -E "complex" | cut -c1-140; done
