@@ -823,7 +823,11 @@ int xe_launch(XEngine *x, const void *d_in, int T, int Fstride, int f_off, int32
         const int groups = (x->F + ch - 1) / ch;
         const int threads = (ch * q.nblk + 31) / 32 * 32;
         // enough CTAs for ~4 per SM: split the integration into time slices when there are few channel groups
-        int ts = std::max(1, std::min((4 * sms + groups - 1) / groups, (T + 4 * C32_TT - 1) / (4 * C32_TT)));
+        static const int per_sm = [] {
+            const char *e = getenv("CLB200_XE_C32_CTAS");       // tuning
+            return e && atoi(e) > 0 ? atoi(e) : 4;
+        }();
+        int ts = std::max(1, std::min((per_sm * sms + groups - 1) / groups, (T + 4 * C32_TT - 1) / (4 * C32_TT)));
         ts = std::min(ts, 64);
         q.ts = ts;
         if (ts > 1) {
