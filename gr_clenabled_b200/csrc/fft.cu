@@ -545,13 +545,26 @@ k_fft_col(const void *__restrict__ in, float2 *__restrict__ out, long nvec, int 
             __syncthreads();                                           // the last pass has read its inputs
             for_each_output<P, EPT>(x, lt, [&](int k, float2 a) { buf[P::pad(k)] = a; });
             __syncthreads();
-            for (int i = threadIdx.x; i < C * NA; i += T * C) {
-                const int col = i >> LOGN, k = i & (NA - 1);
-                float2 a = smem[col * LINE + P::pad(k)];
-                // W_N^(n2 k1) = W_N^(512 hi) * W_N^lo: two L1-resident tables of <= 512 entries, one rounding
-                const unsigned ph = ((unsigned)(c0 + col) * (unsigned)k) & (unsigned)(n - 1);
-                a = cmul(a, cmul(__ldg(tw4 + 512 + (ph >> 9)), __ldg(tw4 + (ph & 511))));
-                __stcs(out + base + (long)(c0 + col) * NA + k, a);
+            // W_N^(n2 k1) = W_N^(512 hi) * W_N^lo from two L1-resident tables of <= 512 entries for every fourth column,
+            // the three columns in between by multiplying with W_N^k1 (at most three extra roundings): the table reads
+            // were as many LSU wavefronts as the data itself
+            auto wn = [&](unsigned ph) {
+                ph &= (unsigned)(n - 1);
+                return cmul(__ldg(tw4 + 512 + (ph >> 9)), __ldg(tw4 + (ph & 511)));
+            };
+#pragma unroll
+            for (int kk = 0; kk < NA / (T * C) + (NA % (T * C) != 0); kk++) {
+                const int k = threadIdx.x + kk * T * C;
+                if (k >= NA) break;
+                const float2 step = wn((unsigned)k);
+                float2 w = make_float2(1.f, 0.f);
+#pragma unroll
+                for (int col = 0; col < C; col++) {
+                    if (col % 4 == 0) w = wn((unsigned)(c0 + col) * (unsigned)k);
+                    else w = cmul(w, step);
+                    const float2 a = cmul(smem[col * LINE + P::pad(k)], w);
+                    __stcs(out + base + (long)(c0 + col) * NA + k, a);
+                }
             }
         }
     }

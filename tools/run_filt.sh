@@ -1,1 +1,2 @@
-for c in 2 3 4 5 6 8; do echo "ctas/SM target $c"; CLB200_XE_C32_CTAS=$c timeout 300 python tools/time_blocks.py 2>&1 | grep -E "complex" | cut -c1-120; done
+timeout 300 python -m pytest tests -m gpu -x -q -k "above_16384 or multi_kernel or not_a_power" 2>&1 | tail -2
+timeout 300 python tools/fft_big_ab.py 2>&1
