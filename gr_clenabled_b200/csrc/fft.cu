@@ -281,6 +281,75 @@ k_fft_pf(const float2 *__restrict__ in, float2 *__restrict__ out, long nvec,
     }
 }
 
+// The two transforms of the chirp-z path (lengths that are not a power of two, fft_launch_blue) with its element-wise
+// steps fused in: STAGE 0 reads the caller's n-point vectors (window, real input, backward half swap, conjugation for
+// the backward transform), multiplies by the chirp, zero-pads to the 2^LOGN-point block and transforms it; STAGE 1
+// multiplies the block by the resident spectrum of the wrapped conj(chirp) on load, runs the inverse transform and
+// stores the first n outputs times the chirp (forward half swap fused).  Four crossings of HBM instead of ten.
+struct FftCz {
+    const float2 *chirp;     // w[k], k < n
+    const float2 *bspec;     // FFT_m of the wrapped conj(w), pre-scaled by 1/m
+    const float *win;        // or null
+    int n, real_in, inverse, swap_h;
+};
+__device__ __forceinline__ int cz_swap(int p, int h) { return p < h ? p + h : (p < 2 * h ? p - h : p); }
+
+template <int LOGN, int EPT, int BATCH, int MINB, int STAGE>
+__global__ void __launch_bounds__((1 << LOGN) / EPT * BATCH, MINB)
+k_fft_cz(const void *__restrict__ in, float2 *__restrict__ out, long nvec, const float2 *__restrict__ tw, FftCz cz)
+{
+    using P = Plan<LOGN, EPT>;
+    constexpr int N = P::N, T = P::T;
+    extern __shared__ __align__(16) float2 smem[];
+    const int tb = (BATCH == 1) ? 0 : threadIdx.x / T;
+    const int lt = (BATCH == 1) ? threadIdx.x : threadIdx.x % T;
+    float2 *buf = smem + tb * P::SMEM_F2;
+    const int n = cz.n;
+    const long ntile = (nvec + BATCH - 1) / BATCH;
+    for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long v = tile * BATCH + tb;
+        const bool active = v < nvec;
+        float2 x[EPT];
+        static_for<0, EPT>([&](auto e_) {
+            constexpr int e = decltype(e_)::value;
+            const int idx = in_index<P, EPT>(lt, e);
+            float2 a = make_float2(0.f, 0.f);
+            if (STAGE == 0) {
+                if (active && idx < n) {
+                    const int src = cz.swap_h ? cz_swap(idx, cz.swap_h) : idx;
+                    a = cz.real_in ? make_float2(__ldcs(reinterpret_cast<const float *>(in) + v * n + src), 0.f)
+                                   : ldg_stream(reinterpret_cast<const float2 *>(in) + v * n + src);
+                    if (cz.win != nullptr) {
+                        const float w = __ldg(cz.win + idx);
+                        a.x *= w;
+                        a.y *= w;
+                    }
+                    if (cz.inverse) a.y = -a.y;
+                    a = cmul(a, __ldg(cz.chirp + idx));
+                }
+            } else {
+                if (active) {
+                    a = cmul(ldg_stream(reinterpret_cast<const float2 *>(in) + v * N + idx), __ldg(cz.bspec + idx));
+                    a = make_float2(a.y, a.x);                          // inverse transform = forward on swapped re/im
+                }
+            }
+            x[e] = a;
+        });
+        fft_core<P, EPT>(x, buf, lt, tw);
+        if (active) {
+            for_each_output<P, EPT>(x, lt, [&](int k, float2 a) {
+                if (STAGE == 0) {
+                    __stcs(out + v * N + k, a);
+                } else if (k < n) {
+                    a = cmul(make_float2(a.y, a.x), __ldg(cz.chirp + k));
+                    if (cz.inverse) a.y = -a.y;
+                    __stcs(out + v * n + (cz.swap_h ? cz_swap(k, cz.swap_h) : k), a);
+                }
+            });
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host ----
 struct FftVariant {
     int logn, ept, batch, threads, smem_bytes, tw_total, max_ctas_per_sm;
@@ -292,6 +361,7 @@ struct FftVariant {
     void (*kernel_d[3])(const float2 *, float2 *, long, const float2 *, const float *, int, unsigned long long *);    // tiles from the work counter (multi-pass sizes) or null
     void (*kernel_u[3])(const float2 *, float2 *, long, const float2 *, const float *, int, unsigned long long *);    // the same, loop form 2
     int tw1_bytes;
+    void (*kernel_cz[2])(const void *, float2 *, long, const float2 *, FftCz);    // chirp-z stages (fft_launch_blue)
 };
 
 template <int LOGN, int EPT>
@@ -333,6 +403,8 @@ FftVariant make_variant()
     v.kernel[2] = &k_fft<LOGN, EPT, BATCH, MINB, 2>;     // forward, real input
     v.kernel_pf[0] = v.kernel_pf[1] = nullptr;
     v.kernel_xc = &k_xcfft<LOGN, EPT, BATCH, MINB>;
+    v.kernel_cz[0] = &k_fft_cz<LOGN, EPT, BATCH, MINB, 0>;
+    v.kernel_cz[1] = &k_fft_cz<LOGN, EPT, BATCH, MINB, 1>;
     v.kernel_d[0] = v.kernel_d[1] = v.kernel_d[2] = nullptr;
     // measured per size on B200 (tools/fft_dyn_ab.py -> profiles/r2_tile_ab.txt), round-1 instantiation with static
     // striding = 100 %: with tiles of >= 2048 samples and the fewest passes (64: 8x8 x 32 transforms per CTA, 128: 16x8,
@@ -398,8 +470,8 @@ struct Fft : clb200_block {
     Buf d_twA, d_twB, d_tw4;     // twiddles of the two column plans; W_N^j (j < 512) followed by W_N^(512 j) (j < N / 512)
     int col_resident[2] = {1, 1};
     // sizes that are not a power of two: chirp-z (Bluestein) on top of two power-of-two plans of m >= 2n-1 points
-    bool blue = false;
-    int m = 0;
+    bool blue = false, blue_fused = false;
+    int m = 0, blue_resident = 1;
     Buf d_chirp, d_bspec;        // w[n] = e^{-i pi n^2 / N} (n floats2), FFT_m of the wrapped conj(w), pre-scaled by 1/m
     int n1 = 0, n2 = 0;
     clb200_handle sub1 = nullptr, sub2 = nullptr;      // n1- and n2-point plans (complex, no window, no shift)
@@ -672,6 +744,24 @@ __global__ void __launch_bounds__(256) k_blue_post(const float2 *__restrict__ c,
 int fft_launch_blue(Fft *f, const void *d_in, void *d_out, long nvec, cudaStream_t st)
 {
     int rc = CLB200_OK;
+    Fft *s1 = static_cast<Fft *>(f->sub1);
+    if (f->blue_fused && s1->var) {
+        // m <= 16384: the two in-SM transforms with the element-wise steps fused in (k_fft_cz), one scratch buffer
+        Fft::Scratch *sc = fft_scratch(f, st, (size_t)nvec * f->m * sizeof(float2), &rc);
+        if (!sc) return rc;
+        const FftVariant *v = s1->var;
+        const long ntile = (nvec + v->batch - 1) / v->batch;
+        const int grid = grid_for(ntile, device_sm_count(f->device), f->blue_resident);
+        const int inverse = f->dir > 0, h = f->n / 2;
+        FftCz cz{(const float2 *)f->d_chirp.p, (const float2 *)f->d_bspec.p, f->has_window ? (const float *)f->d_win.p : nullptr,
+                 f->n, f->dtype == CLB200_DTYPE_FLOAT, inverse, (f->shift && inverse) ? h : 0};
+        v->kernel_cz[0]<<<grid, v->threads, v->smem_bytes, st>>>(d_in, (float2 *)sc->a.p, nvec, (const float2 *)s1->d_tw.p, cz);
+        cz.swap_h = (f->shift && !inverse) ? h : 0;
+        v->kernel_cz[1]<<<grid, v->threads, v->smem_bytes, st>>>(sc->a.p, (float2 *)d_out, nvec, (const float2 *)s1->d_tw.p, cz);
+        CLB_CUDA(cudaGetLastError());
+        f->n_launch += 2;
+        return CLB200_OK;
+    }
     Fft::Scratch *sc = fft_scratch(f, st, (size_t)nvec * f->m * sizeof(float2), &rc);
     if (!sc) return rc;
     float2 *ta = (float2 *)sc->a.p, *tb = (float2 *)sc->b.p;
@@ -1059,8 +1149,29 @@ int clb200_fft_create(int fft_size, int dir, const float *window, int window_len
         int rc = clb200_fft_create(m, CLB200_FFT_FORWARD, nullptr, 0, CLB200_DTYPE_COMPLEX, device, 0, &f->sub1);
         if (rc == CLB200_OK) rc = clb200_fft_create(m, CLB200_FFT_BACKWARD, nullptr, 0, CLB200_DTYPE_COMPLEX, device, 0, &f->sub2);
         if (rc != CLB200_OK) return fail(rc);
-        f->set_info("clFFT %d-pt %s: not a power of two -> chirp-z (Bluestein) over %d-point plans, window / half swaps fused "
-                    "into the pre- and post-multiply", fft_size, dir < 0 ? "forward" : "backward", m);
+        {
+            // both stages fused into the two in-SM transforms when m fits one CTA (CLB200_FFT_CZ_UNFUSED=1 for A/B)
+            const char *e = getenv("CLB200_FFT_CZ_UNFUSED");
+            Fft *s1 = static_cast<Fft *>(f->sub1);
+            if (!(e && atoi(e)) && s1->var) {
+                int occ0 = 0, occ1 = 0;
+                const void *k0 = (const void *)s1->var->kernel_cz[0], *k1 = (const void *)s1->var->kernel_cz[1];
+                if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, s1->var->smem_bytes) == cudaSuccess &&
+                    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, s1->var->smem_bytes) == cudaSuccess &&
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k0, s1->var->threads, s1->var->smem_bytes) == cudaSuccess &&
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, s1->var->threads, s1->var->smem_bytes) == cudaSuccess &&
+                    occ0 >= 1 && occ1 >= 1) {
+                    f->blue_fused = true;
+                    f->blue_resident = std::min(occ0, occ1);
+                }
+                cudaGetLastError();
+            }
+        }
+        f->set_info("clFFT %d-pt %s: not a power of two -> chirp-z (Bluestein) over %d-point plans, %s", fft_size,
+                    dir < 0 ? "forward" : "backward", m,
+                    f->blue_fused ? "pre-multiply / zero-pad fused into the forward transform, spectrum product and post-multiply "
+                                    "into the inverse one (two kernels)"
+                                  : "window / half swaps fused into the pre- and post-multiply kernels (five kernels)");
         *out = f;
         return CLB200_OK;
     }
