@@ -98,6 +98,25 @@ k_map1(const float4 *__restrict__ in, float4 *__restrict__ out, long nvec, long 
     }
 }
 
+// Scheduler-sized launches (the zero-copy path of run_chunked: the pointers are pinned HOST memory): one vector per
+// thread, 64-thread CTAs -- an SM keeps only a few reads of system memory in flight (one CTA needs 110 us for 64 KiB,
+// profiles/r2_mailbox_probe.txt), so the call's 4096 vectors go to 64 SMs instead of 4.
+template <class F>
+__global__ void __launch_bounds__(64)
+k_map1_small(const float4 *__restrict__ in, float4 *__restrict__ out, long nvec, long nscalar, F f)
+{
+    const long i = (long)blockIdx.x * 64 + threadIdx.x;
+    if (i < nvec) st4(out + i, f.vec(ld4(in + i)));
+    if (blockIdx.x == 0) {
+        long t = nvec * 4 + threadIdx.x;
+        if (t < nscalar) {
+            const float *si = reinterpret_cast<const float *>(in);
+            float *so = reinterpret_cast<float *>(out);
+            so[t] = f.scalar(si[t], (int)(t & 1));
+        }
+    }
+}
+
 // unaligned fallback: plain scalar grid-stride
 template <class F>
 __global__ void __launch_bounds__(EW_THREADS)
@@ -145,6 +164,11 @@ int launch_map1(const void *in, void *out, long nfloats, F f, int sms, cudaStrea
     bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
     if (aligned) {
         long nvec = nfloats / 4;
+        if (nvec > 0 && nvec <= 64L * 1024) {                    // <= 1 MiB: spread over as many SMs as there are
+            k_map1_small<F><<<(unsigned)((nvec + 63) / 64), 64, 0, st>>>((const float4 *)in, (float4 *)out, nvec, nfloats, f);
+            CLB_CUDA(cudaGetLastError());
+            return CLB200_OK;
+        }
         long ctas = (nvec + EW_THREADS * EW_UNROLL - 1) / (EW_THREADS * EW_UNROLL);
         int grid = grid_for(ctas, sms, EW_CTAS_PER_SM);
         k_map1<F><<<grid, EW_THREADS, 0, st>>>((const float4 *)in, (float4 *)out, nvec, nfloats, f,
