@@ -576,7 +576,8 @@ const FiltVariant *pick_filt(int ntaps)
     v10c.kernel = &k_fftfilt_r<10, 32, 152>;
     v10d.kernel = &k_fftfilt_r<10, 32, 144>;
     v10e.kernel = &k_fftfilt_r<10, 32, 136>;
-    static const FiltVariant v12 = make_filt<12, 16, 2>();    // 4096 = 16^3 (register hand-over)
+    static const FiltVariant v12 = make_filt<12, 16, 3>();    // 4096 = 16^3 (register hand-over), three CTAs per SM (+3 % over
+                                                              // two; 32 x 32 x 4 with a shared-memory re-order measured slower)
     static const FiltVariant v14 = make_filt<14, 32, 1>();    // 16384 = 32 * 32 * 16, 512 threads (16^3 * 4 with 1024 threads and
                                                               // 64 registers measured 18 % slower: 1.38 vs 1.69 TB/s at 3000 taps)
     const char *e = getenv("CLB200_FILT_NF");                 // tuning: force the block size
