@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 k_map2(const float4 *__restrict__ a, const float4 *__restrict__ b, float4 *__restrict__ c,
        long nvec, Bin f, unsigned long long *wq)
 {
-    constexpr int U = 2;                                  // two vectors per operand in flight per thread
+    constexpr int U = 4;                                  // four vectors per operand in flight per thread
     ew_tile_loop<U>(nvec, wq,
         [&](long i) {
             float4 va[U], vb[U];
@@ -257,7 +257,7 @@ int launch_map2(const void *a, const void *b, void *c, long nfloats, Bin f, int 
     bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
     long nvec = aligned ? nfloats / 4 : 0;
     if (nvec > 0) {
-        long ctas = (nvec + EW_THREADS * 2 - 1) / (EW_THREADS * 2);
+        long ctas = (nvec + EW_THREADS * 4 - 1) / (EW_THREADS * 4);
         const int grid = grid_for(ctas, sms, EW_CTAS_PER_SM);
         k_map2<<<grid, EW_THREADS, 0, st>>>((const float4 *)a, (const float4 *)b, (float4 *)c, nvec, f,
                                             (blk && ctas > 2L * grid) ? blk->work_counter(st) : nullptr);
