@@ -437,7 +437,7 @@ FftVariant make_variant()
 const FftVariant *pick_variant(int logn)
 {
     static const FftVariant tab[] = {
-        make_variant<1, 2, 32, 24>(),   make_variant<2, 4, 32, 24>(),  make_variant<3, 8, 32, 16>(),
+        make_variant<1, 2, 256, 8>(),   make_variant<2, 4, 32, 24>(),  make_variant<3, 8, 32, 16>(),
         make_variant<4, 4, 8, 24>(),    make_variant<5, 8, 8, 24>(),   make_variant<6, 8, 32, 2>(),
         make_variant<7, 16, 16, 4>(),   make_variant<8, 16, 16, 2>(),  make_variant<9, 32, 16, 2>(),
         make_variant<10, 32, 8, 2>(),   make_variant<11, 32, 4, 2>(),  make_variant<12, 16, 1, 2>(),
