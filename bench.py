@@ -342,10 +342,12 @@ def secondary_blocks(torch, blocks, capi, dev, stream_ptr, hbm_peak):
     except Exception as e:                           # noqa: BLE001
         out["clPolyphaseChannelizer_64ch"] = {"error": str(e)}
     try:
-        # clFFT outside the one-kernel sizes: 65536 points (two passes of column transforms) and 10000 points (not a
-        # power of two: chirp-z over 32768-point plans); 16 B/sample algorithmic like the headline
-        for name, N in (("clFFT_65536pt_two_pass", 65536), ("clFFT_10000pt_chirpz", 10000)):
-            nv = (1 << 24) // N if N == 10000 else n // N
+        # clFFT outside the one-kernel sizes: 65536 points (two passes of column transforms), 1000 points (not a power
+        # of two: fused chirp-z over 2048-point transforms) and 10000 points (chirp-z over 32768-point two-pass plans);
+        # 16 B/sample algorithmic like the headline
+        for name, N in (("clFFT_65536pt_two_pass", 65536), ("clFFT_1000pt_chirpz_two_kernels", 1000),
+                        ("clFFT_10000pt_chirpz_five_kernels", 10000)):
+            nv = (1 << 24) // N if N != 65536 else n // N
             blk = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *gpu)
             t = _timeit(torch, lambda: blk.launch_device(a.data_ptr(), b.data_ptr(), nv, stream_ptr), 3)
             out[name] = hbm(16 * nv * N, t, nv * N)
