@@ -407,10 +407,11 @@ FftVariant make_variant()
     v.kernel_cz[1] = &k_fft_cz<LOGN, EPT, BATCH, MINB, 1>;
     v.kernel_d[0] = v.kernel_d[1] = v.kernel_d[2] = nullptr;
     // measured per size on B200 (tools/fft_dyn_ab.py -> profiles/r2_tile_ab.txt), round-1 instantiation with static
-    // striding = 100 %: with tiles of >= 2048 samples and the fewest passes (64: 8x8 x 32 transforms per CTA, 128: 16x8,
-    // 512: 32x16, 1024: 32x32, 2048: 32x32x2) and work-counter tiles -- 64 points 116 %, 128: 111 %, 256: 114 %, 512: 108 %,
-    // 1024: 119 %, 2048: 107 %, 4096: 107 %, 8192: 110 %, 16384: 105 % (loop form 2); 16 and 32 points keep their small
-    // static tiles (larger or dynamic ones measured slower)
+    // striding = 100 %: with tiles of >= 2048 samples, the fewest passes and -- where the transform allows 128-thread
+    // CTAs -- four CTAs per SM (64: 8x8 x 32 transforms per CTA, 128: 16x8, 512: 32x16, 1024: 32x32, 2048: 32x32x2 with
+    // two transforms per 128-thread CTA, 4096: 32x32x4 with one) and work-counter tiles -- 64 points 116 %, 128: 111 %,
+    // 256: 114 %, 512: 108 %, 1024: 119 %, 2048: 120 %, 4096: 115 %, 8192: 110 %, 16384: 105 % (loop form 2); 16 and 32
+    // points keep their small static tiles (larger or dynamic ones measured slower)
     if constexpr (P::npass() > 1 && fft_loop_form(LOGN) == 1) {
         v.kernel_d[0] = &k_fft<LOGN, EPT, BATCH, MINB, 8>;
         v.kernel_d[1] = &k_fft<LOGN, EPT, BATCH, MINB, 9>;
@@ -440,7 +441,7 @@ const FftVariant *pick_variant(int logn)
         make_variant<1, 2, 256, 8>(),   make_variant<2, 4, 32, 24>(),  make_variant<3, 8, 32, 16>(),
         make_variant<4, 4, 8, 24>(),    make_variant<5, 8, 8, 24>(),   make_variant<6, 8, 32, 2>(),
         make_variant<7, 16, 16, 4>(),   make_variant<8, 16, 16, 2>(),  make_variant<9, 32, 16, 2>(),
-        make_variant<10, 32, 8, 2>(),   make_variant<11, 32, 4, 2>(),  make_variant<12, 16, 1, 2>(),
+        make_variant<10, 32, 8, 2>(),   make_variant<11, 32, 2, 4>(),  make_variant<12, 32, 1, 4>(),
         make_variant<13, 32, 1, 2>(),   make_variant<14, 32, 1, 1>(),
     };
     if (logn < 1 || logn > 14) return nullptr;
