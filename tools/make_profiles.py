@@ -57,6 +57,7 @@ d = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from t
                  "(%s_*_full.txt); bench.py copies the clFFT figure into roofline.traffic when its launch shape matches" % R}
 XE = 32 * 1024 * 1024 * 2 + 1024 * 528 * 8
 for rep, dst, key, alg in (("fft.ncu-rep", "fft8192_full.txt", "k_fft_8192pt_x8192vec", 1073741824),
+                           ("fft4096.ncu-rep", "fft4096_full.txt", "k_fft_4096pt_x16384vec", 1073741824),
                            ("fftfilt.ncu-rep", "fftfilt_full.txt", "k_fftfilt_256tap_64Mi", 1073741824),
                            ("fir.ncu-rep", "fir_full.txt", "k_fir_256tap_64Mi", 1073741824),
                            ("pfb.ncu-rep", "pfb_full.txt", "k_pfb_64ch_64Mi", 1073741824),

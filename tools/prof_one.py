@@ -12,8 +12,9 @@ what = sys.argv[1]
 sp = torch.cuda.current_stream().cuda_stream
 gpu = (1, 1, 0, 0)
 reps = int(os.environ.get("REPS", "3"))
-if what == "fft":
-    N, nvec = 8192, 8192
+if what in ("fft", "fft4096"):
+    N = 8192 if what == "fft" else 4096
+    nvec = (1 << 26) // N
     x = torch.empty(N * nvec * 2, dtype=torch.float32, device="cuda").uniform_(-1, 1)
     y = torch.empty_like(x)
     f = blocks.clFFT(N, capi.FFT_FORWARD, [], capi.DTYPE_COMPLEX, *gpu)

@@ -8,6 +8,7 @@ cap k_xengine_tma xe_batch xengine_batch
 cap k_xengine_tma xe_pk xengine_packed
 cap k_xengine_c32 xe_c32 xengine_c32
 cap "^k_fft$" fft fft
+cap "^k_fft$" fft4096 fft4096
 cap k_fftfilt fftfilt filter
 cap k_fir fir fir
 cap k_pfb pfb pfb
